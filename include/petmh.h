@@ -1,0 +1,135 @@
+/* petmh.h -- C ABI of libpetmh.so: B200-native batched Metropolis-Hastings posterior
+ * sampler for the SRTM2 PET kinetic model.
+ *
+ * Drop-in boundary for ONE path of yanisdjebra/PET_posterior_distribution: the MCMC
+ * baseline `mcmc.py` (element-wise Metropolis, mcmc.py:147-157) over the SRTM2 forward
+ * model of `kinetic_model.py` (kinetic_model.py:12-57, 134-158).  Each entry point
+ * names the reference interface it replaces.  The reference is pure Python, so the
+ * reference-side binding is a ctypes stub.
+ *
+ * Conventions: every function returns 0 on success, a negative PETMH_E* code on error
+ * (message via petmh_last_error).  The caller owns every buffer.  All pointers are HOST
+ * pointers, row-major, unless the name says `_device`.  A handle is bound to one CUDA
+ * device and one stream and is not thread-safe.  There is NO CPU fallback: create fails
+ * with PETMH_ENODEVICE when no sm_100 device is present.
+ *
+ * Fixed shapes of the path: R = 48 ROIs, T = 54 frames (the reference's acquisition
+ * grid, sample_sim_data.py:29-85), state = (DVR[48], R1[48]) per chain.
+ */
+#ifndef PETMH_H
+#define PETMH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PETMH_N_ROI 48
+#define PETMH_N_FRAMES 54
+#define PETMH_N_COORD 96   /* DVR[48] then R1[48] */
+#define PETMH_N_STATS 8    /* columns of the summary table, see petmh_get_summary */
+
+#define PETMH_OK 0
+#define PETMH_EINVAL (-1)     /* bad argument / call order */
+#define PETMH_ENODEVICE (-2)  /* no sm_100 CUDA device (there is no CPU fallback) */
+#define PETMH_ECUDA (-3)      /* CUDA runtime error */
+#define PETMH_ENOMEM (-4)
+#define PETMH_EGRID (-5)      /* frame grid's operator sparsity differs from the compiled schedule */
+
+typedef struct petmh_handle petmh_t;
+
+typedef struct {
+    int32_t device;        /* CUDA ordinal */
+    int32_t n_chains;      /* chains per TAC (mcmc.py:58 `chains`, honoured here)            */
+    int32_t max_tacs;      /* capacity: test TACs resident at once                            */
+    int32_t max_draws;     /* stored (thinned) draws per chain; 0 = running moments only      */
+    uint64_t seed;         /* Philox key                                                      */
+    uint64_t tac_gid0;     /* global index of local TAC 0 (multi-GPU shards keep their streams) */
+} petmh_cfg;
+
+/* ---- lifetime -------------------------------------------------------------------- */
+int petmh_create(const petmh_cfg* cfg, petmh_t** out);
+void petmh_destroy(petmh_t* h);
+const char* petmh_last_error(const petmh_t* h); /* h may be NULL: error of a failed create */
+int petmh_version(void);
+
+/* ---- model inputs ------------------------------------------------------------------ */
+/* replaces SRTM2.__init__(frame_time_list, frame_duration_list, .) kinetic_model.py:136-140
+ * (frame END times and durations in minutes; mcmc.py:73-74). */
+int petmh_set_frames(petmh_t* h, const double* t54, const double* dt54);
+/* replaces pm.MvNormal("var_DVR", mu, cov) / ("var_R1", ...) mcmc.py:148-149 */
+int petmh_set_prior(petmh_t* h, const double* mu_dvr48, const double* cov_dvr48x48,
+                    const double* mu_r1_48, const double* cov_r1_48x48);
+/* replaces the per-sample setup mcmc.py:106-112,133-134,153-155:
+ *   y[n_tac][48][54]   = tac_noisy_sampled / dt  (mcmc.py:79-80,109)
+ *   tac_ref[n_tac][54] = vartacref[sample]       (mcmc.py:133-134)
+ *   k2p[n_tac]         = km_obs['k2p'][0]        (mcmc.py:150)
+ *   sigma_noise[48][54] shared by all TACs       (mcmc.py:96,153) */
+int petmh_set_data(petmh_t* h, int n_tac, const double* y, const double* tac_ref,
+                   const double* k2p, const double* sigma_noise);
+/* same, float32 inputs (bulk path for large batches; pinned memory recommended);
+ * sigma_noise may be NULL to keep the previous one. */
+int petmh_set_data_f32(petmh_t* h, int n_tac, const float* y, const float* tac_ref,
+                       const float* k2p, const float* sigma_noise);
+
+/* ---- parity hooks ------------------------------------------------------------------ */
+/* replaces CreateTAC_SRTM2.perform (mcmc.py:38-39) == SRTM2.create_activity_curve(...).T
+ * (kinetic_model.py:142-158): out[48][54], unclamped. */
+int petmh_forward(petmh_t* h, int tac, const double* dvr48, const double* r1_48, double* out48x54);
+/* replaces the model log-probability pieces (mcmc.py:148-155): ll48[i] = sum_t log
+ * TruncatedNormal(y_it | mu=sn_it, sigma=sqrt(sn_it) sigma_noise_it, lower=0) including the
+ * state-independent constants; logprior2 = {log MvNormal(DVR), log MvNormal(R1)}. */
+int petmh_loglik(petmh_t* h, int tac, const double* dvr48, const double* r1_48, double* ll48,
+                 double* logprior2);
+/* the device-built exact convolution operator M (54x54) of estimate_continuous_convolution
+ * (kinetic_model.py:12-32): conv = M @ exp(-k2a t). */
+int petmh_get_operator(petmh_t* h, int tac, double* m54x54);
+/* raw Philox4x32-10 words the kernel draws for (chain gid, sweep, block): out[48][4] */
+int petmh_philox_raw(petmh_t* h, uint64_t chain_gid, uint32_t sweep, uint32_t block, uint32_t* out48x4);
+
+/* ---- sampling (replaces pm.sample(draws, tune, step=pm.Metropolis(...)) mcmc.py:156-157) --- */
+/* Start all chains at the prior mean with scaling 1 (pymc defaults), sweep counter 0. */
+int petmh_reset(petmh_t* h);
+/* tune sweeps with pymc's scaling table every 100 sweeps, then draws sweeps with frozen
+ * scaling; every thin-th draw is stored when max_draws > 0; running moments always.
+ * One sweep = 96 chain-steps per chain.  Equivalent to reset + plan + advance(tune+draws). */
+int petmh_run(petmh_t* h, int draws, int tune, int thin);
+/* Lower level: declare the schedule (sweeps [0,tune) tune, [tune,tune+draws) are draws),
+ * then continue every chain for n_sweeps at a time (checkpointable between calls). */
+int petmh_plan(petmh_t* h, int draws, int tune, int thin);
+int petmh_advance(petmh_t* h, int n_sweeps);
+/* Teacher-forcing / decision-parity mode: like petmh_run for the first n_tape_chains chains
+ * of TAC `tac` only, consuming an explicit random tape instead of Philox:
+ *   normals[c][s][2][48] f32, logu[c][s][2][48] f32, rank[c][s][2][48] u8 (visit position)
+ * and recording every sweep: draws_out[c][s][2][48] f32, optional delta_out (f32, the
+ * log acceptance ratio at decision time) and accept_out (u8), scale_out[c][2][48] f32. */
+int petmh_run_taped(petmh_t* h, int tac, int n_tape_chains, int n_sweeps, int tune,
+                    const float* normals, const float* logu, const uint8_t* rank,
+                    float* draws_out, float* delta_out, uint8_t* accept_out, float* scale_out);
+
+/* ---- outputs (replaces idata.posterior[...] / pm.summary / pm.rhat mcmc.py:162-187) ---- */
+int petmh_n_stored(const petmh_t* h); /* stored draws per chain so far */
+/* dvr/r1: [n_tac][n_chains][n_stored][48] float32 (DVR_mcmc / R1_mcmc, mcmc.py:162-163) */
+int petmh_get_chains(petmh_t* h, float* dvr, float* r1);
+/* out[n_tac][96][PETMH_N_STATS] f32: mean, sd, mcse_mean, ess_bulk, ess_tail, r_hat,
+ * accept_rate, scaling -- from stored draws when max_draws > 0 (rank-normalised split
+ * R-hat / ESS as ArviZ), else from running split-half moments (classic split R-hat,
+ * batch-means ESS; ess_tail = NaN). */
+int petmh_get_summary(petmh_t* h, float* out);
+/* same, written to a DEVICE buffer (e.g. a slice of an NCCL all-gather buffer) on
+ * `stream` (a cudaStream_t, 0 = the handle's). */
+int petmh_summary_device(petmh_t* h, float* d_out, void* stream);
+int petmh_get_state(petmh_t* h, float* q /*[n_tac][n_chains][96]*/, float* scale /*same*/);
+
+/* ---- timing / stream ------------------------------------------------------------- */
+int petmh_set_stream(petmh_t* h, void* cuda_stream);
+int petmh_synchronize(petmh_t* h);
+/* CUDA-event time of the sweep-kernel launches of the last run/advance, and their count */
+int petmh_last_kernel_ms(const petmh_t* h, float* ms, int* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PETMH_H */

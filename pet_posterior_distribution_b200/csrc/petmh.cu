@@ -1,0 +1,695 @@
+// petmh.cu -- host side of libpetmh.so: the C ABI declared in include/petmh.h.
+// Device code: petmh_device.cuh (sweep kernel) and petmh_diag.cuh (diagnostics).
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/petmh.h"
+#include "petmh_device.cuh"
+#include "petmh_diag.cuh"
+
+using namespace petmh;
+
+static std::string g_create_error;
+
+struct petmh_handle {
+    petmh_cfg cfg{};
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    // model
+    bool have_frames = false, have_prior = false, have_data = false, have_noise = false;
+    FrameTables ft_host{};
+    FrameTables* d_ft = nullptr;
+    float tcol[NCOL]{};
+    double t[NT]{}, dt[NT]{};
+    double mu[2][48]{}, logdet[2]{};
+    std::vector<double> P;   // [2][48][48]
+    double* d_P = nullptr;
+    double* d_mu = nullptr;
+    float* d_cc = nullptr;
+    double ll_const[48]{};   // sum_t -log(sigma_noise) - log sqrt(2 pi)
+    // data
+    int n_tac = 0;
+    float* d_y = nullptr;
+    double* d_cref = nullptr;
+    float* d_k2p = nullptr;
+    // state
+    float *d_q = nullptr, *d_scale = nullptr, *d_mom = nullptr, *d_draws = nullptr;
+    uint8_t* d_cnt = nullptr;
+    uint32_t* d_nacc = nullptr;
+    // schedule
+    int plan_draws = 0, plan_tune = 0, plan_thin = 1;
+    int sweep = 0;
+    int mom_n[2] = {0, 0};        // draws merged per half
+    int mom_launches[2] = {0, 0}; // launches per half (each contributes nb-1 lag terms)
+    // scratch for hooks
+    float* d_scratch = nullptr;   // >= 48*54 + 48 + 96 floats
+    double* d_scratch64 = nullptr;
+    // timing
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0.f;
+    int last_launches = 0;
+    int launch_sweeps = 200;
+};
+
+static int fail(petmh_t* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(h, PETMH_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" int petmh_version(void) { return 100; }
+
+extern "C" const char* petmh_last_error(const petmh_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+// ------------------------------------------------------------------------------------
+// frame tables: linear-interpolation weights exactly as interp1d_linear_vec
+// (kinetic_model.py:41-49): searchsorted-left index hi, lo = hi-1 (wraps at -1), weight
+// |xp[lo]-x| on hi and |xp[hi]-x| on lo, normalised.
+// ------------------------------------------------------------------------------------
+static void two_tap(const double* xp, int np, double x, int& ia, double& wa, int& ib, double& wb) {
+    int hi = 0;
+    while (hi < np && xp[hi] < x) hi++;          // searchsorted(side='left')
+    int lo = hi - 1;
+    if (lo < 0) lo += np;                         // numpy negative index wraps
+    if (hi >= np) hi = np - 1;                    // cannot happen for x <= max(xp)
+    double w_hi = std::fabs(xp[lo] - x), w_lo = std::fabs(xp[hi] - x);
+    if (lo == hi) { w_hi = 1.0; w_lo = 0.0; }
+    const double s = w_hi + w_lo;
+    ia = lo; wa = w_lo / s;
+    ib = hi; wb = w_hi / s;
+}
+
+static int build_frame_tables(petmh_t* h, const double* t) {
+    FrameTables& ft = h->ft_host;
+    double tmin = t[0], tmax = t[0];
+    for (int i = 0; i < NT; i++) {
+        if (i && !(t[i] > t[i - 1])) return fail(h, PETMH_EINVAL, "frame times must be strictly increasing");
+        tmin = std::min(tmin, t[i]);
+        tmax = std::max(tmax, t[i]);
+    }
+    double x[NGRID];                              // np.linspace(min, max, 2*54)
+    const double step = (tmax - tmin) / (NGRID - 1);
+    for (int i = 0; i < NGRID; i++) x[i] = tmin + i * step;
+    x[NGRID - 1] = tmax;
+    ft.dx = x[1] - x[0];
+    for (int i = 0; i < NGRID; i++) two_tap(t, NT, x[i], ft.fa[i], ft.fwa[i], ft.fb[i], ft.fwb[i]);
+    for (int j = 0; j < NT; j++) two_tap(x, NGRID, t[j], ft.ba[j], ft.bwa[j], ft.bb[j], ft.bwb[j]);
+    for (int f = 0; f < NT; f++) {
+        ft.klo[f] = NGRID; ft.khi[f] = -1;
+        for (int k = 0; k < NGRID; k++) {
+            const bool hit = (ft.fa[k] == f && ft.fwa[k] != 0.0) || (ft.fb[k] == f && ft.fwb[k] != 0.0);
+            if (hit) { ft.klo[f] = std::min(ft.klo[f], k); ft.khi[f] = std::max(ft.khi[f], k); }
+        }
+    }
+    // structural pattern of M and comparison with the compiled schedule
+    static const int acol_c[NCOL] = PETMH_ACTIVE_COLS;
+    static const int nrow_c[NT] = PETMH_NROW_PREFIX;
+    static const short pack_c[MPACK] = PETMH_MPACK_SRC;
+    bool nz[NT][NT];
+    for (int j = 0; j < NT; j++)
+        for (int f = 0; f < NT; f++) {
+            bool any = false;
+            for (int side = 0; side < 2 && !any; side++) {
+                const int i = side ? ft.bb[j] : ft.ba[j];
+                const double w = side ? ft.bwb[j] : ft.bwa[j];
+                if (w == 0.0) continue;
+                if (ft.klo[f] <= std::min(ft.khi[f], i)) any = true;
+            }
+            nz[j][f] = any;
+        }
+    for (int j = 0; j < NT; j++) {
+        int cnt = 0;
+        for (int f = 0; f < NT; f++) cnt += nz[j][f];
+        bool ok = cnt == nrow_c[j];
+        for (int c = 0; c < nrow_c[j] && ok; c++) ok = nz[j][acol_c[c]];
+        if (!ok)
+            return fail(h, PETMH_EGRID,
+                        "frame grid not supported: sparsity of the convolution operator (row %d) differs from the "
+                        "compiled 54-frame schedule (tools/gen_schedule.py)", j);
+    }
+    for (int c = 0; c < NCOL; c++) { ft.acol[c] = acol_c[c]; h->tcol[c] = (float)t[acol_c[c]]; }
+    for (int i = 0; i < MPACK; i++) ft.pack_src[i] = pack_c[i];
+    return PETMH_OK;
+}
+
+// symmetric positive-definite inverse + log-determinant via Cholesky (fp64)
+static bool spd_inverse(const double* a, int n, double* inv, double* logdet) {
+    std::vector<double> L(n * n, 0.0);
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j <= i; j++) {
+            double s = a[i * n + j];
+            for (int k = 0; k < j; k++) s -= L[i * n + k] * L[j * n + k];
+            if (i == j) {
+                if (!(s > 0.0)) return false;
+                L[i * n + i] = std::sqrt(s);
+            } else
+                L[i * n + j] = s / L[j * n + j];
+        }
+    *logdet = 0.0;
+    for (int i = 0; i < n; i++) *logdet += 2.0 * std::log(L[i * n + i]);
+    std::vector<double> Li(n * n, 0.0);   // L^-1
+    for (int c = 0; c < n; c++) {
+        for (int i = c; i < n; i++) {
+            double s = (i == c) ? 1.0 : 0.0;
+            for (int k = c; k < i; k++) s -= L[i * n + k] * Li[k * n + c];
+            Li[i * n + c] = s / L[i * n + i];
+        }
+    }
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j <= i; j++) {
+            double s = 0.0;
+            for (int k = i; k < n; k++) s += Li[k * n + i] * Li[k * n + j];
+            inv[i * n + j] = inv[j * n + i] = s;
+        }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------
+extern "C" int petmh_create(const petmh_cfg* cfg, petmh_t** out) {
+    petmh_t* h = nullptr;
+    if (!cfg || !out) return fail(nullptr, PETMH_EINVAL, "null argument");
+    if (cfg->n_chains < 1 || cfg->max_tacs < 1 || cfg->max_draws < 0)
+        return fail(nullptr, PETMH_EINVAL, "n_chains and max_tacs must be >= 1, max_draws >= 0");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, PETMH_ENODEVICE, "no CUDA device: libpetmh has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, PETMH_EINVAL, "device ordinal out of range");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10)
+        return fail(nullptr, PETMH_ENODEVICE, "device %d is not sm_100 (Blackwell B200): kernels are built for sm_100a only",
+                    cfg->device);
+    h = new petmh_handle();
+    h->cfg = *cfg;
+    if (const char* e = getenv("PETMH_LAUNCH_SWEEPS")) h->launch_sweeps = std::max(1, atoi(e));
+    auto bail = [&](int code) { petmh_destroy(h); return code; };
+#define CUC(call)                                                                                     \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            fail(nullptr, e_ == cudaErrorMemoryAllocation ? PETMH_ENOMEM : PETMH_ECUDA, "%s failed: %s", #call, \
+                 cudaGetErrorString(e_));                                                             \
+            return bail(e_ == cudaErrorMemoryAllocation ? PETMH_ENOMEM : PETMH_ECUDA);                \
+        }                                                                                             \
+    } while (0)
+    CUC(cudaSetDevice(cfg->device));
+    CUC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+    CUC(cudaEventCreate(&h->ev0));
+    CUC(cudaEventCreate(&h->ev1));
+    const size_t S = cfg->max_tacs, NC = S * (size_t)cfg->n_chains;
+    CUC(cudaMalloc(&h->d_ft, sizeof(FrameTables)));
+    CUC(cudaMalloc(&h->d_P, 2 * 48 * 48 * sizeof(double)));
+    CUC(cudaMalloc(&h->d_mu, 2 * 48 * sizeof(double)));
+    CUC(cudaMalloc(&h->d_cc, 48 * NT * sizeof(float)));
+    CUC(cudaMalloc(&h->d_y, S * 48 * NT * sizeof(float)));
+    CUC(cudaMalloc(&h->d_cref, S * NT * sizeof(double)));
+    CUC(cudaMalloc(&h->d_k2p, S * sizeof(float)));
+    CUC(cudaMalloc(&h->d_q, NC * 96 * sizeof(float)));
+    CUC(cudaMalloc(&h->d_scale, NC * 96 * sizeof(float)));
+    CUC(cudaMalloc(&h->d_cnt, NC * 96));
+    CUC(cudaMalloc(&h->d_nacc, NC * 96 * sizeof(uint32_t)));
+    CUC(cudaMalloc(&h->d_mom, NC * 96 * 6 * sizeof(float)));
+    if (cfg->max_draws > 0) CUC(cudaMalloc(&h->d_draws, NC * (size_t)cfg->max_draws * 96 * sizeof(float)));
+    CUC(cudaMalloc(&h->d_scratch, (48 * NT + 256) * sizeof(float)));
+    CUC(cudaMalloc(&h->d_scratch64, NT * NT * sizeof(double)));
+    CUC(cudaFuncSetAttribute(mh_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(256)));
+    CUC(cudaFuncSetAttribute(forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_MOM + 32 * SLOTS * NT * 4));
+#undef CUC
+    *out = h;
+    return PETMH_OK;
+}
+
+extern "C" void petmh_destroy(petmh_t* h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    void* bufs[] = {h->d_ft, h->d_P, h->d_mu, h->d_cc, h->d_y, h->d_cref, h->d_k2p, h->d_q, h->d_scale,
+                    h->d_cnt, h->d_nacc, h->d_mom, h->d_draws, h->d_scratch, h->d_scratch64};
+    for (void* b : bufs) if (b) cudaFree(b);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int petmh_set_stream(petmh_t* h, void* s) {
+    if (!h) return PETMH_EINVAL;
+    if (h->own_stream && h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    h->stream = (cudaStream_t)s;
+    h->own_stream = false;
+    return PETMH_OK;
+}
+extern "C" int petmh_synchronize(petmh_t* h) {
+    if (!h) return PETMH_EINVAL;
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaStreamSynchronize(h->stream));
+    return PETMH_OK;
+}
+extern "C" int petmh_last_kernel_ms(const petmh_t* h, float* ms, int* launches) {
+    if (!h) return PETMH_EINVAL;
+    if (ms) *ms = h->last_ms;
+    if (launches) *launches = h->last_launches;
+    return PETMH_OK;
+}
+
+extern "C" int petmh_set_frames(petmh_t* h, const double* t54, const double* dt54) {
+    if (!h || !t54 || !dt54) return fail(h, PETMH_EINVAL, "null argument");
+    CU(cudaSetDevice(h->cfg.device));
+    int rc = build_frame_tables(h, t54);
+    if (rc) return rc;
+    memcpy(h->t, t54, sizeof h->t);
+    memcpy(h->dt, dt54, sizeof h->dt);
+    CU(cudaMemcpyAsync(h->d_ft, &h->ft_host, sizeof(FrameTables), cudaMemcpyHostToDevice, h->stream));
+    {   // one frame grid per process (c_tcol is module-wide constant memory)
+        static bool loaded = false;
+        static float loaded_tcol[NCOL];
+        if (loaded && memcmp(loaded_tcol, h->tcol, sizeof loaded_tcol) != 0)
+            return fail(h, PETMH_EINVAL, "a different frame grid is already loaded in this process");
+        CU(cudaMemcpyToSymbolAsync(c_tcol, h->tcol, sizeof h->tcol, 0, cudaMemcpyHostToDevice, h->stream));
+        memcpy(loaded_tcol, h->tcol, sizeof loaded_tcol);
+        loaded = true;
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    h->have_frames = true;
+    return PETMH_OK;
+}
+
+extern "C" int petmh_set_prior(petmh_t* h, const double* mu_dvr, const double* cov_dvr, const double* mu_r1,
+                               const double* cov_r1) {
+    if (!h || !mu_dvr || !cov_dvr || !mu_r1 || !cov_r1) return fail(h, PETMH_EINVAL, "null argument");
+    CU(cudaSetDevice(h->cfg.device));
+    h->P.assign(2 * 48 * 48, 0.0);
+    const double* covs[2] = {cov_dvr, cov_r1};
+    const double* mus[2] = {mu_dvr, mu_r1};
+    for (int b = 0; b < 2; b++) {
+        memcpy(h->mu[b], mus[b], 48 * sizeof(double));
+        if (!spd_inverse(covs[b], 48, h->P.data() + b * 48 * 48, &h->logdet[b]))
+            return fail(h, PETMH_EINVAL, "prior covariance %d is not positive definite", b);
+    }
+    CU(cudaMemcpyAsync(h->d_P, h->P.data(), 2 * 48 * 48 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_mu, h->mu, 2 * 48 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->have_prior = true;
+    return PETMH_OK;
+}
+
+static int upload_noise(petmh_t* h, const double* sig) {
+    std::vector<float> cc(48 * NT);
+    for (int r = 0; r < 48; r++) {
+        double c = 0.0;
+        for (int j = 0; j < NT; j++) {
+            const double s = sig[r * NT + j];
+            if (!(s > 0.0)) return fail(h, PETMH_EINVAL, "sigma_noise must be > 0");
+            cc[r * NT + j] = (float)(1.0 / (s * std::sqrt(2.0)));
+            c += -std::log(s) - 0.5 * std::log(2.0 * M_PI);
+        }
+        h->ll_const[r] = c;
+    }
+    CU(cudaMemcpyAsync(h->d_cc, cc.data(), cc.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->have_noise = true;
+    return PETMH_OK;
+}
+
+extern "C" int petmh_set_data(petmh_t* h, int n_tac, const double* y, const double* tac_ref, const double* k2p,
+                              const double* sigma_noise) {
+    if (!h || !y || !tac_ref || !k2p) return fail(h, PETMH_EINVAL, "null argument");
+    if (n_tac < 1 || n_tac > h->cfg.max_tacs) return fail(h, PETMH_EINVAL, "n_tac %d outside [1, max_tacs=%d]", n_tac, h->cfg.max_tacs);
+    CU(cudaSetDevice(h->cfg.device));
+    if (sigma_noise) { int rc = upload_noise(h, sigma_noise); if (rc) return rc; }
+    if (!h->have_noise) return fail(h, PETMH_EINVAL, "sigma_noise never set");
+    const size_t ny = (size_t)n_tac * 48 * NT, nc = (size_t)n_tac * NT, nk = n_tac;
+    double *dy = nullptr, *dc = nullptr, *dk = nullptr;
+    CU(cudaMallocAsync(&dy, ny * sizeof(double), h->stream));
+    CU(cudaMallocAsync(&dc, nc * sizeof(double), h->stream));
+    CU(cudaMallocAsync(&dk, nk * sizeof(double), h->stream));
+    CU(cudaMemcpyAsync(dy, y, ny * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(dc, tac_ref, nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(dk, k2p, nk * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    convert_data_kernel<<<(unsigned)((ny + 255) / 256), 256, 0, h->stream>>>(dy, dc, dk, h->d_y, h->d_cref, h->d_k2p, ny, nc, nk);
+    CU(cudaGetLastError());
+    CU(cudaFreeAsync(dy, h->stream));
+    CU(cudaFreeAsync(dc, h->stream));
+    CU(cudaFreeAsync(dk, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->n_tac = n_tac;
+    h->have_data = true;
+    return PETMH_OK;
+}
+
+extern "C" int petmh_set_data_f32(petmh_t* h, int n_tac, const float* y, const float* tac_ref, const float* k2p,
+                                  const float* sigma_noise) {
+    if (!h || !y || !tac_ref || !k2p) return fail(h, PETMH_EINVAL, "null argument");
+    if (n_tac < 1 || n_tac > h->cfg.max_tacs) return fail(h, PETMH_EINVAL, "n_tac %d outside [1, max_tacs=%d]", n_tac, h->cfg.max_tacs);
+    CU(cudaSetDevice(h->cfg.device));
+    if (sigma_noise) {
+        std::vector<double> s(48 * NT);
+        for (int i = 0; i < 48 * NT; i++) s[i] = sigma_noise[i];
+        int rc = upload_noise(h, s.data());
+        if (rc) return rc;
+    }
+    if (!h->have_noise) return fail(h, PETMH_EINVAL, "sigma_noise never set");
+    const size_t ny = (size_t)n_tac * 48 * NT, nc = (size_t)n_tac * NT;
+    float* dc = nullptr;
+    CU(cudaMallocAsync(&dc, nc * sizeof(float), h->stream));
+    CU(cudaMemcpyAsync(h->d_y, y, ny * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(dc, tac_ref, nc * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_k2p, k2p, (size_t)n_tac * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    convert_data_f32_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, h->stream>>>(dc, h->d_cref, nc);
+    CU(cudaGetLastError());
+    CU(cudaFreeAsync(dc, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->n_tac = n_tac;
+    h->have_data = true;
+    return PETMH_OK;
+}
+
+static int check_ready(petmh_t* h) {
+    if (!h) return PETMH_EINVAL;
+    if (!h->have_frames) return fail(h, PETMH_EINVAL, "petmh_set_frames not called");
+    if (!h->have_prior) return fail(h, PETMH_EINVAL, "petmh_set_prior not called");
+    if (!h->have_data) return fail(h, PETMH_EINVAL, "petmh_set_data not called");
+    return PETMH_OK;
+}
+
+static SweepParams base_params(petmh_t* h) {
+    SweepParams p{};
+    p.ft = h->d_ft;
+    p.P = h->d_P;
+    p.mu = h->d_mu;
+    p.cc = h->d_cc;
+    p.y = h->d_y;
+    p.cref = h->d_cref;
+    p.k2p = h->d_k2p;
+    p.q = h->d_q;
+    p.scale = h->d_scale;
+    p.cnt = h->d_cnt;
+    p.draws = h->d_draws;
+    p.mom = h->d_mom;
+    p.nacc = h->d_nacc;
+    p.max_draws = h->cfg.max_draws;
+    p.n_tacs = h->n_tac;
+    p.n_chains = h->cfg.n_chains;
+    p.thin = 1;
+    p.seed = h->cfg.seed;
+    p.tac_gid0 = h->cfg.tac_gid0;
+    return p;
+}
+
+// ---- parity hooks ----------------------------------------------------------------------
+static int run_forward(petmh_t* h, int tac, const double* dvr, const double* r1, std::vector<float>& tac_out,
+                       std::vector<float>& ll_out) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (tac < 0 || tac >= h->n_tac) return fail(h, PETMH_EINVAL, "tac index out of range");
+    CU(cudaSetDevice(h->cfg.device));
+    float in[96];
+    for (int i = 0; i < 48; i++) { in[i] = (float)dvr[i]; in[48 + i] = (float)r1[i]; }
+    float* d_in = h->d_scratch + 48 * NT + 64;
+    CU(cudaMemcpyAsync(d_in, in, sizeof in, cudaMemcpyHostToDevice, h->stream));
+    SweepParams p = base_params(h);
+    forward_kernel<<<1, 64, SM_MOM + 32 * SLOTS * NT * 4, h->stream>>>(p, tac, d_in, d_in + 48, h->d_scratch, h->d_scratch + 48 * NT);
+    CU(cudaGetLastError());
+    tac_out.resize(48 * NT);
+    ll_out.resize(48);
+    CU(cudaMemcpyAsync(tac_out.data(), h->d_scratch, 48 * NT * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(ll_out.data(), h->d_scratch + 48 * NT, 48 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return PETMH_OK;
+}
+
+extern "C" int petmh_forward(petmh_t* h, int tac, const double* dvr48, const double* r1_48, double* out48x54) {
+    if (!h || !dvr48 || !r1_48 || !out48x54) return fail(h, PETMH_EINVAL, "null argument");
+    std::vector<float> t, l;
+    int rc = run_forward(h, tac, dvr48, r1_48, t, l);
+    if (rc) return rc;
+    for (int i = 0; i < 48 * NT; i++) out48x54[i] = t[i];
+    return PETMH_OK;
+}
+
+extern "C" int petmh_loglik(petmh_t* h, int tac, const double* dvr48, const double* r1_48, double* ll48,
+                            double* logprior2) {
+    if (!h || !dvr48 || !r1_48 || !ll48) return fail(h, PETMH_EINVAL, "null argument");
+    std::vector<float> t, l;
+    int rc = run_forward(h, tac, dvr48, r1_48, t, l);
+    if (rc) return rc;
+    for (int i = 0; i < 48; i++) ll48[i] = (double)l[i] + h->ll_const[i];
+    if (logprior2) {
+        const double* q[2] = {dvr48, r1_48};
+        for (int b = 0; b < 2; b++) {
+            double quad = 0.0;
+            for (int i = 0; i < 48; i++) {
+                double s = 0.0;
+                for (int j = 0; j < 48; j++) s += h->P[(b * 48 + i) * 48 + j] * (q[b][j] - h->mu[b][j]);
+                quad += (q[b][i] - h->mu[b][i]) * s;
+            }
+            logprior2[b] = -0.5 * quad - 0.5 * h->logdet[b] - 24.0 * std::log(2.0 * M_PI);
+        }
+    }
+    return PETMH_OK;
+}
+
+extern "C" int petmh_get_operator(petmh_t* h, int tac, double* m) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!m || tac < 0 || tac >= h->n_tac) return fail(h, PETMH_EINVAL, "bad argument");
+    CU(cudaSetDevice(h->cfg.device));
+    SweepParams p = base_params(h);
+    operator_kernel<<<1, 256, 0, h->stream>>>(p, tac, h->d_scratch64);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(m, h->d_scratch64, NT * NT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return PETMH_OK;
+}
+
+extern "C" int petmh_philox_raw(petmh_t* h, uint64_t gid, uint32_t sweep, uint32_t block, uint32_t* out) {
+    if (!h || !out) return fail(h, PETMH_EINVAL, "null argument");
+    CU(cudaSetDevice(h->cfg.device));
+    uint32_t* d = reinterpret_cast<uint32_t*>(h->d_scratch);
+    philox_kernel<<<1, 64, 0, h->stream>>>(h->cfg.seed, gid, sweep, block, d);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, d, 48 * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return PETMH_OK;
+}
+
+// ---- sampling --------------------------------------------------------------------------
+extern "C" int petmh_reset(petmh_t* h) {
+    if (!h) return PETMH_EINVAL;
+    if (!h->have_prior) return fail(h, PETMH_EINVAL, "petmh_set_prior not called");
+    CU(cudaSetDevice(h->cfg.device));
+    const size_t NC = (size_t)h->cfg.max_tacs * h->cfg.n_chains;
+    const size_t n = NC * 96 * 6;
+    init_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_q, h->d_scale, h->d_cnt, h->d_nacc, h->d_mom, h->d_mu, NC);
+    CU(cudaGetLastError());
+    h->sweep = 0;
+    h->mom_n[0] = h->mom_n[1] = 0;
+    h->mom_launches[0] = h->mom_launches[1] = 0;
+    return PETMH_OK;
+}
+
+extern "C" int petmh_plan(petmh_t* h, int draws, int tune, int thin) {
+    if (!h) return PETMH_EINVAL;
+    if (draws < 0 || tune < 0 || thin < 1) return fail(h, PETMH_EINVAL, "draws/tune must be >= 0 and thin >= 1");
+    h->plan_draws = draws;
+    h->plan_tune = tune;
+    h->plan_thin = thin;
+    return PETMH_OK;
+}
+
+static int threads_per_cta(const petmh_t* h) {
+    int t = h->cfg.n_chains * 16;
+    t = (t + 31) / 32 * 32;
+    return std::min(t, 256);
+}
+
+extern "C" int petmh_advance(petmh_t* h, int n_sweeps) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (n_sweeps < 0) return fail(h, PETMH_EINVAL, "n_sweeps < 0");
+    CU(cudaSetDevice(h->cfg.device));
+    const int nthr = threads_per_cta(h);
+    const int chains_per_cta = nthr / 16;
+    const int groups = (h->cfg.n_chains + chains_per_cta - 1) / chains_per_cta;
+    const unsigned grid = (unsigned)((size_t)h->n_tac * groups);
+    const int half_at = h->plan_tune + (h->plan_draws + 1) / 2;   // first sweep of the second half
+    int left = n_sweeps;
+    h->last_launches = 0;
+    CU(cudaEventRecord(h->ev0, h->stream));
+    while (left > 0) {
+        int n = std::min(left, h->launch_sweeps);
+        // do not straddle the tune/draw boundary or the half boundary
+        if (h->sweep < h->plan_tune) n = std::min(n, h->plan_tune - h->sweep);
+        else if (h->sweep < half_at) n = std::min(n, half_at - h->sweep);
+        SweepParams p = base_params(h);
+        p.sweep0 = h->sweep;
+        p.n_sweeps = n;
+        p.tune_until = h->plan_tune;
+        p.thin = h->plan_thin;
+        const bool drawing = h->sweep >= h->plan_tune;
+        const int half = (drawing && h->sweep >= half_at) ? 1 : 0;
+        p.mom_half = half;
+        p.mom_n_before = h->mom_n[half];
+        mh_sweep_kernel<<<grid, nthr, smem_bytes(nthr), h->stream>>>(p);
+        CU(cudaGetLastError());
+        if (drawing) { h->mom_n[half] += n; h->mom_launches[half] += 1; }
+        h->sweep += n;
+        left -= n;
+        h->last_launches++;
+    }
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaEventSynchronize(h->ev1));
+    CU(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    return PETMH_OK;
+}
+
+extern "C" int petmh_run(petmh_t* h, int draws, int tune, int thin) {
+    int rc = petmh_reset(h);
+    if (rc) return rc;
+    rc = petmh_plan(h, draws, tune, thin);
+    if (rc) return rc;
+    return petmh_advance(h, draws + tune);
+}
+
+extern "C" int petmh_run_taped(petmh_t* h, int tac, int n_tape_chains, int n_sweeps, int tune, const float* normals,
+                               const float* logu, const uint8_t* rank, float* draws_out, float* delta_out,
+                               uint8_t* accept_out, float* scale_out) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!normals || !logu || !rank || !draws_out) return fail(h, PETMH_EINVAL, "null argument");
+    if (tac < 0 || tac >= h->n_tac || n_tape_chains < 1 || n_sweeps < 1 || tune < 0 || tune > n_sweeps)
+        return fail(h, PETMH_EINVAL, "bad taped-run arguments");
+    CU(cudaSetDevice(h->cfg.device));
+    const size_t n = (size_t)n_tape_chains * n_sweeps * 96;
+    float *dn = nullptr, *dl = nullptr, *dd = nullptr, *ddelta = nullptr, *dscale = nullptr;
+    uint8_t *dr = nullptr, *dacc = nullptr;
+    CU(cudaMalloc(&dn, n * 4)); CU(cudaMalloc(&dl, n * 4)); CU(cudaMalloc(&dr, n));
+    CU(cudaMalloc(&dd, n * 4)); CU(cudaMalloc(&ddelta, n * 4)); CU(cudaMalloc(&dacc, n));
+    CU(cudaMalloc(&dscale, (size_t)n_tape_chains * 96 * 4));
+    CU(cudaMemcpyAsync(dn, normals, n * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(dl, logu, n * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(dr, rank, n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemsetAsync(ddelta, 0, n * 4, h->stream));
+    CU(cudaMemsetAsync(dacc, 0, n, h->stream));
+    SweepParams p = base_params(h);
+    p.n_chains = n_tape_chains;
+    p.scale = dscale;
+    p.draws = nullptr;
+    p.sweep0 = 0;
+    p.n_sweeps = n_sweeps;
+    p.tune_until = tune;
+    p.tape_n = dn; p.tape_logu = dl; p.tape_rank = dr;
+    p.dbg_draws = dd; p.dbg_delta = ddelta; p.dbg_accept = dacc;
+    p.tape_tac = tac; p.tape_sweeps = n_sweeps;
+    int nthr = std::min(256, (n_tape_chains * 16 + 31) / 32 * 32);
+    const int cpc = nthr / 16;
+    const unsigned grid = (unsigned)((n_tape_chains + cpc - 1) / cpc);
+    mh_sweep_kernel<<<grid, nthr, smem_bytes(nthr), h->stream>>>(p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(draws_out, dd, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (delta_out) CU(cudaMemcpyAsync(delta_out, ddelta, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (accept_out) CU(cudaMemcpyAsync(accept_out, dacc, n, cudaMemcpyDeviceToHost, h->stream));
+    if (scale_out) CU(cudaMemcpyAsync(scale_out, dscale, (size_t)n_tape_chains * 96 * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(dn); cudaFree(dl); cudaFree(dr); cudaFree(dd); cudaFree(ddelta); cudaFree(dacc); cudaFree(dscale);
+    return PETMH_OK;
+}
+
+// ---- outputs ---------------------------------------------------------------------------
+extern "C" int petmh_n_stored(const petmh_t* h) {
+    if (!h || h->cfg.max_draws == 0) return 0;
+    const int done = std::max(0, std::min(h->sweep, h->plan_tune + h->plan_draws) - h->plan_tune);
+    return std::min(h->cfg.max_draws, (done + h->plan_thin - 1) / h->plan_thin);
+}
+
+extern "C" int petmh_get_chains(petmh_t* h, float* dvr, float* r1) {
+    if (!h || !dvr || !r1) return fail(h, PETMH_EINVAL, "null argument");
+    if (!h->d_draws) return fail(h, PETMH_EINVAL, "handle created with max_draws = 0: no stored chains");
+    CU(cudaSetDevice(h->cfg.device));
+    const int ns = petmh_n_stored(h);
+    const size_t NC = (size_t)h->n_tac * h->cfg.n_chains;
+    if (ns == 0) return PETMH_OK;
+    // device layout [chain][max_draws][2][48] -> two host arrays [chain][ns][48]
+    for (int b = 0; b < 2; b++) {
+        float* dst = b ? r1 : dvr;
+        if (ns == h->cfg.max_draws) {
+            CU(cudaMemcpy2DAsync(dst, 48 * sizeof(float), h->d_draws + b * 48, 96 * sizeof(float), 48 * sizeof(float),
+                                 NC * (size_t)ns, cudaMemcpyDeviceToHost, h->stream));
+        } else {
+            for (size_t c = 0; c < NC; c++)   // skip the unused slots of every chain
+                CU(cudaMemcpy2DAsync(dst + c * ns * 48, 48 * sizeof(float),
+                                     h->d_draws + c * (size_t)h->cfg.max_draws * 96 + b * 48, 96 * sizeof(float),
+                                     48 * sizeof(float), (size_t)ns, cudaMemcpyDeviceToHost, h->stream));
+        }
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    return PETMH_OK;
+}
+
+extern "C" int petmh_get_state(petmh_t* h, float* q, float* scale) {
+    if (!h) return PETMH_EINVAL;
+    CU(cudaSetDevice(h->cfg.device));
+    const size_t n = (size_t)h->n_tac * h->cfg.n_chains * 96;
+    if (q) CU(cudaMemcpyAsync(q, h->d_q, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (scale) CU(cudaMemcpyAsync(scale, h->d_scale, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return PETMH_OK;
+}
+
+extern "C" int petmh_summary_device(petmh_t* h, float* d_out, void* stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!d_out) return fail(h, PETMH_EINVAL, "null argument");
+    CU(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    if (st != h->stream) CU(cudaStreamSynchronize(h->stream));
+    DiagParams dp{};
+    dp.mom = h->d_mom;
+    dp.mu = h->d_mu;
+    dp.nacc = h->d_nacc;
+    dp.scale = h->d_scale;
+    dp.draws = h->d_draws;
+    dp.n_tacs = h->n_tac;
+    dp.n_chains = h->cfg.n_chains;
+    dp.max_draws = h->cfg.max_draws;
+    dp.n_stored = petmh_n_stored(h);
+    dp.n_half[0] = h->mom_n[0];
+    dp.n_half[1] = h->mom_n[1];
+    dp.lag_terms[0] = h->mom_n[0] - h->mom_launches[0];
+    dp.lag_terms[1] = h->mom_n[1] - h->mom_launches[1];
+    dp.out = d_out;
+    rc = launch_summary(dp, st);
+    if (rc) return fail(h, PETMH_ECUDA, "summary kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+    return PETMH_OK;
+}
+
+extern "C" int petmh_get_summary(petmh_t* h, float* out) {
+    if (!h || !out) return fail(h, PETMH_EINVAL, "null argument");
+    CU(cudaSetDevice(h->cfg.device));
+    const size_t n = (size_t)h->n_tac * 96 * PETMH_N_STATS;
+    float* d = nullptr;
+    CU(cudaMalloc(&d, n * sizeof(float)));
+    int rc = petmh_summary_device(h, d, nullptr);
+    if (rc == PETMH_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, d, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail(h, PETMH_ECUDA, "summary copy failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d);
+    return rc;
+}

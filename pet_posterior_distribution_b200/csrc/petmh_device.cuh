@@ -1,0 +1,744 @@
+// petmh_device.cuh -- sm_100a device code of the batched Metropolis-Hastings sampler.
+//
+// Replaces, for one path of the reference, the Python stack
+//   pm.sample(step=pm.Metropolis) -> delta_logp -> CreateTAC_SRTM2.perform (mcmc.py:27-39,147-157)
+//   -> SRTM2.create_activity_curve -> estimate_continuous_convolution (kinetic_model.py:12-57,142-158)
+// with one fused kernel.  Design notes live in DESIGN.md; the short version:
+//
+//  * The reference "continuous convolution" is an exact linear operator conv = M e,
+//    e_f = exp(-k2a t_f), M (54x54, 1122 nnz, 45 active columns) depending only on the
+//    frame grid and the reference-region TAC.  Each CTA builds its TAC's M in shared
+//    memory (fp64 math, fp32 storage) from c_r in the prologue -- M never touches HBM.
+//  * 16 lanes own one chain, each lane 3 ROIs (i = slot*16 + lane16); a warp = 2 chains.
+//    Phase A (expensive, parallel): every lane evaluates forward model + truncated-normal
+//    log-likelihood at its 3 proposals; the 3 items share every broadcast LDS.128 of M
+//    (register blocking K=3) and the products run as packed fma.rn.f32x2 (FFMA2).
+//    Phase B (cheap, serial in visit order): prior coupling r = P(q-mu) in fp64,
+//    resolved in "first accepted in visit order" rounds with REDUX.MIN + shuffles.
+//  * Philox4x32-10 counter-based randoms keyed by (seed; coord, sweep/block, chain gid).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "m_schedule.inc"
+
+namespace petmh {
+
+constexpr int NROI = 48;
+constexpr int NT = PETMH_T;          // 54 frames
+constexpr int NTP = PETMH_TPAD;      // 56
+constexpr int YS = 60;               // padded row stride (floats) of per-ROI frame arrays in smem
+constexpr int NCOL = PETMH_NCOL;     // 45 active columns of M
+constexpr int NGRID = 2 * NT;        // 108 resample points (kinetic_model.py:14)
+constexpr int MPACK = PETMH_MPACK;
+constexpr int SLOTS = 3;             // ROIs per lane
+constexpr int TUNE_INTERVAL = 100;   // pymc Metropolis tune_interval
+constexpr float Z_CUT = 3.85f;       // erfc(z)/2 < 2^-25 beyond: (1 - h) rounds to 1 in fp32
+constexpr int RB0 = PETMH_ROWBLOCK0, RB1 = PETMH_ROWBLOCK1, RB2 = PETMH_ROWBLOCK2;
+constexpr int NPAIR = (RB1 - RB0) / 2;  // accumulator pairs per row block (both blocks equal)
+static_assert(RB2 - RB1 == RB1 - RB0, "row blocks must have equal size");
+static_assert(PETMH_NBLOCKS == 2, "kernel written for two row blocks");
+
+// Frame-grid-only tables (host-built in fp64, see petmh.cu build_frame_tables):
+// W_fwd / W_back of SURVEY.md A.2 in sparse two-tap form.
+struct FrameTables {
+    double dx;                       // resample spacing (kinetic_model.py:18)
+    int fa[NGRID], fb[NGRID];        // W_fwd row i: wa*c[fa] + wb*c[fb]
+    double fwa[NGRID], fwb[NGRID];
+    int ba[NT], bb[NT];              // W_back row j: wa*conv[ba] + wb*conv[bb]
+    double bwa[NT], bwb[NT];
+    int klo[NT], khi[NT];            // grid rows k with W_fwd[k, f] != 0 lie in [klo, khi]
+    int acol[NCOL];                  // active column -> frame index
+    short pack_src[MPACK];           // packed M slot -> (row << 6 | active col) or -1
+};
+
+struct SweepParams {
+    // model constants (per handle)
+    const FrameTables* ft;
+    const double* P;        // [2][48][48] prior precision matrices (fp64)
+    const double* mu;       // [2][48]
+    const float* cc;        // [48][54]  1 / (sigma_noise * sqrt 2)
+    // per-TAC data
+    const float* y;         // [S][48][54]
+    const double* cref;     // [S][54]
+    const float* k2p;       // [S]
+    // chain state [S*C][96]
+    float* q;
+    float* scale;
+    uint8_t* cnt;
+    // outputs
+    float* draws;           // [S*C][max_draws][96] or null
+    float* mom;             // [S*C][2 halves][96][3]: mean - mu, M2, lag-1 co-moment (Chan-merged per launch)
+    int mom_n_before;       // draws already merged into this half
+    uint32_t* nacc;         // [S*C][96] accepted moves in draw sweeps
+    int max_draws;          // capacity (stored draws per chain)
+    int mom_half;           // which half this launch accumulates into
+    int n_tacs, n_chains;
+    int sweep0, n_sweeps, tune_until, thin;
+    unsigned long long seed, tac_gid0;
+    // taped / debug mode (null in production)
+    const float* tape_n;
+    const float* tape_logu;
+    const uint8_t* tape_rank;
+    float* dbg_draws;       // [c][s][96]
+    float* dbg_delta;       // [c][s][96]
+    uint8_t* dbg_accept;    // [c][s][96]
+    int tape_tac, tape_sweeps;
+};
+
+// frame end time (minutes) of each active column of M.  One frame grid per process:
+// petmh_set_frames refuses a second, different grid while it is loaded.
+__constant__ float c_tcol[NCOL];
+
+// ------------------------------------------------------------------------------------
+// small PTX helpers
+// ------------------------------------------------------------------------------------
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// d = a * b + d on two packed fp32 lanes (Blackwell FFMA2)
+__device__ __forceinline__ void ffma2(u64& d, u64 a, u64 b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// ------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011); bit-exact with oracle/philox.py
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+__device__ __forceinline__ float u01(uint32_t x) {  // (0, 1]
+    return fmaf(__uint2float_rn(x), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+}
+
+// ------------------------------------------------------------------------------------
+// 0.5 * erfc(z), z >= 0: t exp(-z^2) Q(t), t = 1/(1 + p z)   (tools/fit_erfc.py, |err| < 2e-7 in fp32)
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ float half_erfc(float z) {
+    const float t = rcp_approx(fmaf(0.389f, z, 1.0f));
+    float qv = -1.149781880e-01f;
+    qv = fmaf(qv, t, 4.521313931e-01f);
+    qv = fmaf(qv, t, -3.312711738e-01f);
+    qv = fmaf(qv, t, 3.342878070e-01f);
+    qv = fmaf(qv, t, 4.196145208e-02f);
+    qv = fmaf(qv, t, 1.178687081e-01f);
+    const float ex = ex2_approx(z * z * -1.4426950408889634f);
+    return qv * t * ex;
+}
+
+// ------------------------------------------------------------------------------------
+// Per-TAC shared-memory image (byte offsets into dynamic shared memory, all 16B aligned)
+// ------------------------------------------------------------------------------------
+constexpr int SM_P = 0;                                   // double [2][48][48]
+constexpr int SM_MU = SM_P + 2 * 48 * 48 * 8;             // double [2][48]
+constexpr int SM_CRS = SM_MU + 2 * 48 * 8;                // double [NGRID]
+constexpr int SM_M = SM_CRS + NGRID * 8;                  // float [MPACK]   packed operator
+constexpr int SM_CR = SM_M + MPACK * 4;                   // float [64]      reference TAC, [60] = k2p
+constexpr int SM_YCC = SM_CR + 64 * 4;                    // float [48][YS]  y * cc
+constexpr int SM_CC = SM_YCC + 48 * YS * 4;               // float [48][YS]  1/(sigma sqrt2)
+constexpr int SM_BAD = SM_CC + 48 * YS * 4;               // uchar [48] (+pad) 1 if any y < 0
+constexpr int SM_MOM = SM_BAD + 64;                       // double [18][nthreads]
+__host__ __device__ constexpr int smem_bytes(int nthreads) { return SM_MOM + 18 * 8 * nthreads; }
+constexpr int K2P_SLOT = 60;
+
+// ------------------------------------------------------------------------------------
+// Phase A: forward model + reduced log-likelihood for the lane's 3 ROIs (l16, l16+16,
+// l16+32) of one TAC, ONE code instance shared by every kernel.
+//   ll = sum_t -(y-s)^2/(2 s sig^2) - log(s)/2 - log(1 - erfc(sqrt(s)/(sig sqrt2))/2)
+// (state-independent constants dropped).  TAC: kinetic_model.py:153-158,
+// clamp + likelihood: mcmc.py:152-155.  tac_out (shared-memory scratch [3][NT] per lane)
+// is only non-null in the parity hook.
+// ------------------------------------------------------------------------------------
+constexpr int K = SLOTS;
+__device__ __noinline__ float3 eval3(const int l16, const float d0, const float d1, const float d2, const float a0,
+                                     const float a1, const float a2, float* tac_out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const float* sM = reinterpret_cast<const float*>(smem + SM_M);
+    const float4* cr4 = reinterpret_cast<const float4*>(smem + SM_CR);
+    const float4* ycc4 = reinterpret_cast<const float4*>(smem + SM_YCC) + l16 * (YS / 4);
+    const float4* cc4 = reinterpret_cast<const float4*>(smem + SM_CC) + l16 * (YS / 4);
+    const float k2p = reinterpret_cast<const float*>(smem + SM_CR)[K2P_SLOT];
+    const float dvr[K] = {d0, d1, d2}, r1[K] = {a0, a1, a2};
+    float na[K], coef[K], G[K], S[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const float k2 = k2p * r1[k];              // kinetic_model.py:153
+        const float k2a = k2 / dvr[k];             // :154
+        coef[k] = fmaf(-r1[k], k2a, k2);           // (k2 - R1*k2a), :157
+        na[k] = k2a * -1.4426950408889634f;        // exp(-k2a t) = 2^(na t)
+        G[k] = 0.f;
+        S[k] = 0.f;
+    }
+
+#define PETMH_ECOL(ci)                                               \
+    {                                                                \
+        _Pragma("unroll") for (int k = 0; k < K; k++) {              \
+            const float e_ = ex2_approx(na[k] * c_tcol[ci]);         \
+            ed[k] = pack2(e_, e_);                                   \
+        }                                                            \
+    }
+#define PETMH_MQ(off, p)                                                              \
+    {                                                                                 \
+        const float4 m_ = *reinterpret_cast<const float4*>(sM + (off));               \
+        const u64 m01_ = pack2(m_.x, m_.y), m23_ = pack2(m_.z, m_.w);                 \
+        _Pragma("unroll") for (int k = 0; k < K; k++) {                               \
+            ffma2(acc[k][p], m01_, ed[k]);                                            \
+            ffma2(acc[k][(p) + 1], m23_, ed[k]);                                      \
+        }                                                                             \
+    }
+#define PETMH_MP(off, p)                                                              \
+    {                                                                                 \
+        const float2 m_ = *reinterpret_cast<const float2*>(sM + (off));               \
+        const u64 m01_ = pack2(m_.x, m_.y);                                           \
+        _Pragma("unroll") for (int k = 0; k < K; k++) ffma2(acc[k][p], m01_, ed[k]);  \
+    }
+
+#pragma unroll
+    for (int blk = 0; blk < 2; blk++) {
+        u64 acc[K][NPAIR];
+        u64 ed[K];
+#pragma unroll
+        for (int k = 0; k < K; k++)
+#pragma unroll
+            for (int p = 0; p < NPAIR; p++) acc[k][p] = 0ull;
+        if (blk == 0) {
+            PETMH_ME_BLOCK0(PETMH_ECOL, PETMH_MQ, PETMH_MP)
+        } else {
+            PETMH_ME_BLOCK1(PETMH_ECOL, PETMH_MQ, PETMH_MP)
+        }
+        const int b0 = blk == 0 ? RB0 : RB1;
+        const int b1 = blk == 0 ? RB1 : RB2;
+        // likelihood for frames b0 .. min(b1, NT)-1 in aligned groups of 4
+#pragma unroll
+        for (int g = b0 / 4; g < b1 / 4; g++) {
+            const float4 crv = cr4[g];
+            const float crj[4] = {crv.x, crv.y, crv.z, crv.w};
+            float zz[K][4], ss[K][4];
+            float zmin = 1e30f;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const float4 yv = ycc4[k * 16 * (YS / 4) + g];
+                const float4 cv = cc4[k * 16 * (YS / 4) + g];
+                const float yj[4] = {yv.x, yv.y, yv.z, yv.w};
+                const float cj[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int j = 4 * g + u;
+                    if (j < NT) {
+                        float lo, hi;
+                        unpack2(acc[k][(j - b0) >> 1], lo, hi);
+                        const float conv = (j & 1) ? hi : lo;
+                        float s = fmaf(coef[k], conv, r1[k] * crj[u]);   // kinetic_model.py:157-158
+                        s = s < 0.f ? 1e-6f : s;                          // mcmc.py:152
+                        const float rs = rsqrt_approx(s);
+                        const float w = fmaf(-s, cj[u], yj[u]);           // (y - s) / (sig sqrt2)
+                        const float uu = w * rs;
+                        G[k] = fmaf(uu, uu, G[k]);                        // (y-s)^2 / (2 s sig^2)
+                        const float z = s * rs * cj[u];                   // sqrt(s) / (sig sqrt2)
+                        zz[k][u] = z;
+                        ss[k][u] = s;
+                        zmin = fminf(zmin, z);
+                    } else {
+                        zz[k][u] = 1e30f;
+                        ss[k][u] = 1.f;
+                    }
+                }
+            }
+            if (tac_out != nullptr) {   // parity hook only (warp-uniform): the unclamped TAC
+#pragma unroll
+                for (int k = 0; k < K; k++)
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int j = 4 * g + u;
+                        if (j < NT) {
+                            float lo, hi;
+                            unpack2(acc[k][(j - b0) >> 1], lo, hi);
+                            tac_out[k * NT + j] = fmaf(coef[k], (j & 1) ? hi : lo, r1[k] * crj[u]);
+                        }
+                    }
+            }
+            // truncation term -log(1 - erfc(z)/2): skipped (warp-uniformly) when every
+            // lane's z >= Z_CUT; the value itself never depends on the neighbours.
+            const bool need = !(zmin >= Z_CUT);   // NaN -> need
+            if (__any_sync(0xffffffffu, need)) {
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    float pr = 1.f;
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const float z = zz[k][u];
+                        const float gsel = (z >= Z_CUT) ? 1.f : (1.f - half_erfc(z));
+                        pr *= ss[k][u] * gsel * gsel;
+                    }
+                    S[k] += lg2_approx(pr);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    const float pr = (ss[k][0] * ss[k][1]) * (ss[k][2] * ss[k][3]);
+                    S[k] += lg2_approx(pr);
+                }
+            }
+        }
+    }
+#undef PETMH_ECOL
+#undef PETMH_MQ
+#undef PETMH_MP
+    const unsigned char* bad = smem + SM_BAD;
+    float out[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const float v = -G[k] - 0.34657359027997264f * S[k];   // -(ln 2)/2 * log2(prod)
+        out[k] = bad[l16 + 16 * k] ? -INFINITY : v;
+    }
+    return make_float3(out[0], out[1], out[2]);
+}
+
+// ------------------------------------------------------------------------------------
+// Prologue helpers: build the per-TAC shared-memory image.
+// ------------------------------------------------------------------------------------
+// c_rs = W_fwd c_r (kinetic_model.py:21), fp64, NGRID values into `crs`.
+__device__ __forceinline__ void build_crs(const FrameTables* ft, const double* __restrict__ cref, double* crs,
+                                          int tid, int nthr) {
+    for (int i = tid; i < NGRID; i += nthr)
+        crs[i] = ft->fwa[i] * cref[ft->fa[i]] + ft->fwb[i] * cref[ft->fb[i]];
+}
+// One entry M[j, f] = dx * sum_{(i,w) in W_back row j} w * sum_{k in [klo_f, min(khi_f, i)]} c_rs[i-k] W_fwd[k,f]
+__device__ __forceinline__ double m_entry(const FrameTables* ft, const double* crs, int j, int f) {
+    double tot = 0.0;
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        const int i = side ? ft->bb[j] : ft->ba[j];
+        const double w = side ? ft->bwb[j] : ft->bwa[j];
+        if (w == 0.0) continue;
+        double s = 0.0;
+        const int kend = min(ft->khi[f], i);
+        for (int k = ft->klo[f]; k <= kend; k++) {
+            double wk = 0.0;
+            if (ft->fa[k] == f) wk += ft->fwa[k];
+            if (ft->fb[k] == f) wk += ft->fwb[k];
+            s = fma(crs[i - k], wk, s);
+        }
+        tot = fma(w, s, tot);
+    }
+    return tot * ft->dx;
+}
+__device__ __forceinline__ void build_M_packed(const FrameTables* ft, const double* crs, float* Mp, int tid,
+                                               int nthr) {
+    for (int idx = tid; idx < MPACK; idx += nthr) {
+        const int src = ft->pack_src[idx];
+        float v = 0.f;
+        if (src >= 0) v = (float)m_entry(ft, crs, src >> 6, ft->acol[src & 63]);
+        Mp[idx] = v;
+    }
+}
+
+__device__ __forceinline__ void load_tac_image(const SweepParams& p, int tac, unsigned char* smem, int tid, int nthr,
+                                               bool with_prior) {
+    double* sP = reinterpret_cast<double*>(smem + SM_P);
+    double* sMu = reinterpret_cast<double*>(smem + SM_MU);
+    double* sCrs = reinterpret_cast<double*>(smem + SM_CRS);
+    float* sM = reinterpret_cast<float*>(smem + SM_M);
+    float* sCr = reinterpret_cast<float*>(smem + SM_CR);
+    float* sYcc = reinterpret_cast<float*>(smem + SM_YCC);
+    float* sCc = reinterpret_cast<float*>(smem + SM_CC);
+    unsigned char* sBad = smem + SM_BAD;
+    if (with_prior) {
+        for (int i = tid; i < 2 * 48 * 48; i += nthr) sP[i] = p.P[i];
+        for (int i = tid; i < 2 * 48; i += nthr) sMu[i] = p.mu[i];
+    }
+    const double* cref = p.cref + (size_t)tac * NT;
+    build_crs(p.ft, cref, sCrs, tid, nthr);
+    for (int i = tid; i < 64; i += nthr) sCr[i] = i < NT ? (float)cref[i] : (i == K2P_SLOT ? p.k2p[tac] : 0.f);
+    if (tid < 48) sBad[tid] = 0;
+    __syncthreads();
+    build_M_packed(p.ft, sCrs, sM, tid, nthr);
+    const float* y = p.y + (size_t)tac * NROI * NT;
+    for (int i = tid; i < NROI * YS; i += nthr) {
+        const int r = i / YS, j = i - r * YS;
+        float c = 0.f, yc = 0.f;
+        if (j < NT) {
+            c = p.cc[r * NT + j];
+            const float yv = y[r * NT + j];
+            yc = yv * c;
+            if (yv < 0.f) sBad[r] = 1;   // benign race: all writers store 1
+        }
+        sCc[i] = c;
+        sYcc[i] = yc;
+    }
+    __syncthreads();
+}
+
+// pymc.step_methods.metropolis.tune as a function of the accept count over 100 sweeps
+__device__ __forceinline__ float tune_factor(int c) {
+    if (c < 1) return 0.1f;      // acc < 0.001
+    if (c < 5) return 0.5f;      // acc < 0.05
+    if (c < 20) return 0.9f;     // acc < 0.2
+    if (c > 95) return 10.0f;    // acc > 0.95
+    if (c > 75) return 2.0f;     // acc > 0.75
+    if (c > 50) return 1.1f;     // acc > 0.5
+    return 1.0f;
+}
+
+// ------------------------------------------------------------------------------------
+// The fused sweep kernel.  blockDim.x = 32*NW; one CTA = 2*NW chains of one TAC.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2) mh_sweep_kernel(const SweepParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const bool TAPED = p.tape_n != nullptr;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int half = lane >> 4, l16 = lane & 15;
+    const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
+    const int chains_per_cta = nthr >> 4;
+    const int groups_per_tac = (p.n_chains + chains_per_cta - 1) / chains_per_cta;
+    const int tac = TAPED ? p.tape_tac : (int)(blockIdx.x / groups_per_tac);
+    const int grp = TAPED ? (int)blockIdx.x : (int)(blockIdx.x % groups_per_tac);
+    const int chain = grp * chains_per_cta + warp * 2 + half;
+    const bool active = chain < p.n_chains;
+    const size_t cg = (size_t)tac * p.n_chains + (active ? chain : 0);   // local chain index (state arrays)
+    const unsigned long long gid = (p.tac_gid0 + (unsigned long long)tac) * (unsigned long long)p.n_chains +
+                                   (unsigned long long)(active ? chain : 0);
+
+    load_tac_image(p, tac, smem, tid, nthr, true);
+    const double* sP = reinterpret_cast<const double*>(smem + SM_P);
+    const double* sMu = reinterpret_cast<const double*>(smem + SM_MU);
+    double* sMom = reinterpret_cast<double*>(smem + SM_MOM);
+#pragma unroll
+    for (int m = 0; m < 18; m++) sMom[m * nthr + tid] = 0.0;
+
+    int roi[SLOTS];
+    float q[2][SLOTS], scale[2][SLOTS];
+    int cnt[2][SLOTS];
+    uint32_t nacc[2][SLOTS];
+#pragma unroll
+    for (int s = 0; s < SLOTS; s++) roi[s] = s * 16 + l16;
+#pragma unroll
+    for (int b = 0; b < 2; b++)
+#pragma unroll
+        for (int s = 0; s < SLOTS; s++) {
+            const size_t o = cg * 96 + b * 48 + roi[s];
+            if (TAPED) {   // pymc start: prior mean, scaling 1
+                q[b][s] = (float)sMu[b * 48 + roi[s]];
+                scale[b][s] = 1.0f;
+                cnt[b][s] = 0;
+            } else {
+                q[b][s] = p.q[o];
+                scale[b][s] = p.scale[o];
+                cnt[b][s] = p.cnt[o];
+            }
+            nacc[b][s] = 0;
+        }
+    // r = P (q - mu) in fp64: stage q of the chain through shuffles
+    double r[2][SLOTS];
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+#pragma unroll
+        for (int s = 0; s < SLOTS; s++) r[b][s] = 0.0;
+#pragma unroll
+        for (int s2 = 0; s2 < SLOTS; s2++) {
+            for (int l2 = 0; l2 < 16; l2++) {
+                const float qv = __shfl_sync(0xffffffffu, q[b][s2], (half << 4) | l2);
+                const int j = s2 * 16 + l2;
+                const double dq = (double)qv - sMu[b * 48 + j];
+#pragma unroll
+                for (int s = 0; s < SLOTS; s++) r[b][s] = fma(sP[(b * 48 + j) * 48 + roi[s]], dq, r[b][s]);
+            }
+        }
+    }
+    float ll_old[SLOTS];
+    {
+        const float3 v = eval3(l16, q[0][0], q[0][1], q[0][2], q[1][0], q[1][1], q[1][2], nullptr);
+        ll_old[0] = v.x; ll_old[1] = v.y; ll_old[2] = v.z;
+    }
+    float prev[2][SLOTS];   // previous recorded draw (lag-1 products)
+#pragma unroll
+    for (int b = 0; b < 2; b++)
+#pragma unroll
+        for (int s = 0; s < SLOTS; s++) prev[b][s] = q[b][s];
+    bool have_prev = false;
+
+    for (int it = 0; it < p.n_sweeps; it++) {
+        const int sweep = p.sweep0 + it;
+        const bool tuning = sweep < p.tune_until;
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            // ---- pymc Metropolis.astep: tune every 100 steps while tuning ----
+            if (tuning && sweep > 0 && (sweep % TUNE_INTERVAL) == 0) {
+#pragma unroll
+                for (int s = 0; s < SLOTS; s++) {
+                    scale[b][s] = __fmul_rn(scale[b][s], tune_factor(cnt[b][s]));
+                    cnt[b][s] = 0;
+                }
+            }
+            // ---- randoms ----
+            float nrm[SLOTS], logu[SLOTS];
+            uint32_t key[SLOTS];
+#pragma unroll
+            for (int s = 0; s < SLOTS; s++) {
+                if (TAPED) {
+                    const size_t o = (((size_t)chain * p.tape_sweeps + sweep) * 2 + b) * 48 + roi[s];
+                    nrm[s] = active ? p.tape_n[o] : 0.f;
+                    logu[s] = active ? p.tape_logu[o] : 0.f;
+                    key[s] = ((active ? (uint32_t)p.tape_rank[o] : (uint32_t)roi[s]) << 6) | (uint32_t)roi[s];
+                } else {
+                    const uint4 x = philox4x32_10(
+                        make_uint4((uint32_t)roi[s], (uint32_t)(2 * sweep + b), (uint32_t)gid, (uint32_t)(gid >> 32)),
+                        make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+                    nrm[s] = sqrtf(-2.f * __logf(u01(x.x))) * __cosf(6.283185307179586f * u01(x.y));
+                    logu[s] = logf(u01(x.z));
+                    key[s] = (x.w & 0xffffffc0u) | (uint32_t)roi[s];
+                }
+            }
+            // ---- proposals: q' = fl32(q + fl32(n * scale)) ----
+            float qn[SLOTS], ll_new[SLOTS];
+#pragma unroll
+            for (int s = 0; s < SLOTS; s++) qn[s] = __fadd_rn(q[b][s], __fmul_rn(nrm[s], scale[b][s]));
+            // ---- phase A ----
+            {
+                const float3 v = b == 0 ? eval3(l16, qn[0], qn[1], qn[2], q[1][0], q[1][1], q[1][2], nullptr)
+                                        : eval3(l16, q[0][0], q[0][1], q[0][2], qn[0], qn[1], qn[2], nullptr);
+                ll_new[0] = v.x; ll_new[1] = v.y; ll_new[2] = v.z;
+            }
+            // ---- phase B: resolve visits in key order ----
+            double d[SLOTS], pre[SLOTS];
+            bool valid[SLOTS];
+#pragma unroll
+            for (int s = 0; s < SLOTS; s++) {
+                d[s] = (double)qn[s] - (double)q[b][s];
+                const float dll = ll_new[s] - ll_old[s];
+                valid[s] = (fabsf(dll) <= 3.0e38f);   // finite (NaN/inf -> false): metrop_select's isfinite
+                // accept iff logu < dll - (d r + d^2 Pii/2)  <=>  pre + d r < 0
+                pre[s] = ((double)logu[s] - (double)dll) + 0.5 * d[s] * d[s] * sP[(b * 48 + roi[s]) * 48 + roi[s]];
+            }
+            uint32_t last = 0;        // keys handled so far are <= last (keys are >= 64 in taped mode? no: rank 0 -> key < 64)
+            bool first_round = true;
+            while (true) {
+                uint32_t cand = 0xffffffffu;
+#pragma unroll
+                for (int s = 0; s < SLOTS; s++) {
+                    const bool open = first_round || key[s] > last;
+                    const bool acc = valid[s] && (fma(d[s], r[b][s], pre[s]) < 0.0);
+                    if (open && acc) cand = min(cand, key[s]);
+                }
+                const uint32_t win = __reduce_min_sync(hmask, cand);
+                if (TAPED) {
+                    if (p.dbg_delta != nullptr && active) {
+#pragma unroll
+                        for (int s = 0; s < SLOTS; s++) {
+                            const bool open = first_round || key[s] > last;
+                            if (open && key[s] <= win) {   // decided in this round
+                                const size_t o = ((size_t)chain * p.tape_sweeps + sweep) * 96 + b * 48 + roi[s];
+                                p.dbg_delta[o] = (float)((double)logu[s] - fma(d[s], r[b][s], pre[s]));
+                                p.dbg_accept[o] = key[s] == win ? 1 : 0;
+                            }
+                        }
+                    }
+                }
+                const bool any_win = win != 0xffffffffu;
+                if (!__any_sync(0xffffffffu, any_win)) break;
+                // broadcast the winner's move and apply it
+                const int wi = (int)(win & 63u);           // winning coordinate (garbage if !any_win)
+                const int wl = wi & 15, ws = wi >> 4;
+                const double dsel = ws == 0 ? d[0] : (ws == 1 ? d[1] : d[2]);
+                const double dw = __shfl_sync(0xffffffffu, dsel, (half << 4) | wl);
+                if (any_win) {
+#pragma unroll
+                    for (int s = 0; s < SLOTS; s++) {
+                        r[b][s] = fma(sP[(b * 48 + wi) * 48 + roi[s]], dw, r[b][s]);
+                        if (key[s] == win) {
+                            q[b][s] = qn[s];
+                            ll_old[s] = ll_new[s];
+                            cnt[b][s] += 1;
+                            if (!tuning) nacc[b][s] += 1;
+                            valid[s] = false;   // spent
+                        }
+                    }
+                    last = win;
+                    first_round = false;
+                } else {
+                    last = 0xfffffffeu;   // this chain is done; keep looping for the other half
+                    first_round = false;
+                }
+            }
+        }
+        // ---- record ----
+        if (TAPED) {
+            if (active) {
+#pragma unroll
+                for (int b = 0; b < 2; b++)
+#pragma unroll
+                    for (int s = 0; s < SLOTS; s++)
+                        p.dbg_draws[((size_t)chain * p.tape_sweeps + sweep) * 96 + b * 48 + roi[s]] = q[b][s];
+            }
+        }
+        if (!tuning) {
+            const int di = sweep - p.tune_until;
+#pragma unroll
+            for (int b = 0; b < 2; b++)
+#pragma unroll
+                for (int s = 0; s < SLOTS; s++) {
+                    const double x = (double)q[b][s] - sMu[b * 48 + roi[s]];
+                    const int m = (b * SLOTS + s) * 3;
+                    sMom[(m + 0) * nthr + tid] += x;
+                    sMom[(m + 1) * nthr + tid] += x * x;
+                    if (have_prev) sMom[(m + 2) * nthr + tid] += x * ((double)prev[b][s] - sMu[b * 48 + roi[s]]);
+                    prev[b][s] = q[b][s];
+                }
+            have_prev = true;
+            if (!TAPED && p.draws != nullptr && active && (di % p.thin) == 0) {
+                const int slot = di / p.thin;
+                if (slot < p.max_draws) {
+#pragma unroll
+                    for (int b = 0; b < 2; b++)
+#pragma unroll
+                        for (int s = 0; s < SLOTS; s++)
+                            p.draws[(cg * p.max_draws + slot) * 96 + b * 48 + roi[s]] = q[b][s];
+                }
+            }
+        }
+    }
+    // ---- epilogue: persist state and moments ----
+    if (active) {
+#pragma unroll
+        for (int b = 0; b < 2; b++)
+#pragma unroll
+            for (int s = 0; s < SLOTS; s++) {
+                const size_t o = cg * 96 + b * 48 + roi[s];
+                if (TAPED) {
+                    p.scale[(size_t)chain * 96 + b * 48 + roi[s]] = scale[b][s];   // scale_out
+                } else {
+                    p.q[o] = q[b][s];
+                    p.scale[o] = scale[b][s];
+                    p.cnt[o] = (uint8_t)cnt[b][s];
+                    p.nacc[o] += nacc[b][s];
+                    const int nb = p.sweep0 + p.n_sweeps - max(p.sweep0, p.tune_until);   // draws this launch
+                    if (nb > 0) {
+                        float* mo = p.mom + ((cg * 2 + p.mom_half) * 96 + b * 48 + roi[s]) * 3;
+                        const int m = (b * SLOTS + s) * 3;
+                        const double sum = sMom[(m + 0) * nthr + tid], sq = sMom[(m + 1) * nthr + tid],
+                                     lag = sMom[(m + 2) * nthr + tid];
+                        const double mean_b = sum / nb, M2_b = sq - sum * mean_b, C1_b = lag - (nb - 1) * mean_b * mean_b;
+                        const double na = p.mom_n_before, n = na + nb;
+                        const double mean_a = mo[0], delta = mean_b - mean_a;
+                        mo[0] = (float)(mean_a + delta * nb / n);
+                        mo[1] = (float)((double)mo[1] + M2_b + delta * delta * na * nb / n);
+                        mo[2] = (float)((double)mo[2] + C1_b);
+                    }
+                }
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Parity-hook kernels (one CTA, 64 threads; lanes 0..15 of warp 0 evaluate 3 ROIs each
+// through exactly the production routine).
+// ------------------------------------------------------------------------------------
+__global__ void forward_kernel(const SweepParams p, int tac, const float* dvr, const float* r1, float* tac_out,
+                               float* ll_out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x;
+    load_tac_image(p, tac, smem, tid, blockDim.x, false);
+    if (tid < 32) {
+        const int l16 = tid & 15;
+        int roi[SLOTS];
+        float a[SLOTS], b[SLOTS], ll[SLOTS];
+#pragma unroll
+        for (int s = 0; s < SLOTS; s++) {
+            roi[s] = s * 16 + l16;
+            a[s] = dvr[roi[s]];
+            b[s] = r1[roi[s]];
+        }
+        float* scratch = reinterpret_cast<float*>(smem + SM_MOM) + tid * SLOTS * NT;
+        const float3 v = eval3(l16, a[0], a[1], a[2], b[0], b[1], b[2], scratch);
+        ll[0] = v.x; ll[1] = v.y; ll[2] = v.z;
+        if (tid < 16) {
+#pragma unroll
+            for (int s = 0; s < SLOTS; s++) {
+                ll_out[roi[s]] = ll[s];
+                for (int j = 0; j < NT; j++) tac_out[roi[s] * NT + j] = scratch[s * NT + j];
+            }
+        }
+    }
+}
+
+__global__ void operator_kernel(const SweepParams p, int tac, double* m_out /*[54][54]*/) {
+    __shared__ double crs[NGRID];
+    build_crs(p.ft, p.cref + (size_t)tac * NT, crs, threadIdx.x, blockDim.x);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < NT * NT; idx += blockDim.x) m_out[idx] = m_entry(p.ft, crs, idx / NT, idx % NT);
+}
+
+__global__ void philox_kernel(unsigned long long seed, unsigned long long gid, uint32_t sweep, uint32_t block,
+                              uint32_t* out) {
+    const int i = threadIdx.x;
+    if (i < 48) {
+        const uint4 x = philox4x32_10(make_uint4((uint32_t)i, 2 * sweep + block, (uint32_t)gid, (uint32_t)(gid >> 32)),
+                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        out[i * 4 + 0] = x.x;
+        out[i * 4 + 1] = x.y;
+        out[i * 4 + 2] = x.z;
+        out[i * 4 + 3] = x.w;
+    }
+}
+
+__global__ void init_state_kernel(float* q, float* scale, uint8_t* cnt, uint32_t* nacc, float* mom, const double* mu,
+                                  size_t n_chains_total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_chains_total * 96) {
+        const int c = (int)(i % 96);
+        q[i] = (float)mu[c];
+        scale[i] = 1.0f;
+        cnt[i] = 0;
+        nacc[i] = 0;
+    }
+    if (i < n_chains_total * 96 * 6) mom[i] = 0.f;
+}
+
+__global__ void convert_data_kernel(const double* y64, const double* cref64, const double* k2p64, float* y, double* cref,
+                                    float* k2p, size_t ny, size_t nc, size_t nk) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ny) y[i] = (float)y64[i];
+    if (i < nc) cref[i] = cref64[i];
+    if (i < nk) k2p[i] = (float)k2p64[i];
+}
+__global__ void convert_data_f32_kernel(const float* cref32, double* cref, size_t nc) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nc) cref[i] = (double)cref32[i];
+}
+
+}  // namespace petmh

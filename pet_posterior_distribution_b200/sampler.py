@@ -1,0 +1,196 @@
+"""MHSampler: thin Python owner of a libpetmh handle (one CUDA device, one stream).
+
+Mirrors, for batches of test TACs, the body of the reference's per-sample loop
+(mcmc.py:104-194): model set-up, pm.sample, chain extraction and summaries.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import N_COORD, N_FRAMES, N_ROI, N_STATS, PetmhError
+
+
+def _d(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _f(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class MHSampler:
+    """Batched element-wise Metropolis sampler for the SRTM2 posterior on one B200.
+
+    n_chains: chains per TAC (the reference's `chains`, mcmc.py:58, honoured here);
+    max_tacs: TACs resident at once; max_draws: stored thinned draws per chain (0 = moments only);
+    tac_gid0: global index of the first local TAC, so Philox streams do not depend on sharding.
+    """
+
+    def __init__(self, n_chains=4, max_tacs=1, max_draws=0, seed=0, device=0, tac_gid0=0):
+        self._h = C.c_void_p()
+        cfg = _lib.Cfg(device, n_chains, max_tacs, max_draws, seed, tac_gid0)
+        rc = _lib.lib.petmh_create(C.byref(cfg), C.byref(self._h))
+        if rc:
+            raise PetmhError(rc, (_lib.lib.petmh_last_error(None) or b"").decode())
+        self.n_chains, self.max_tacs, self.max_draws = n_chains, max_tacs, max_draws
+        self.n_tac = 0
+
+    # -- plumbing -----------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc:
+            raise PetmhError(rc, (_lib.lib.petmh_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib.petmh_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- model --------------------------------------------------------------------------
+    def set_frames(self, time_vector, dt):
+        t = np.ascontiguousarray(time_vector, np.float64)
+        d = np.ascontiguousarray(dt, np.float64)
+        if t.shape != (N_FRAMES,) or d.shape != (N_FRAMES,):
+            raise ValueError("time_vector and dt must have shape (54,)")
+        self._ck(_lib.lib.petmh_set_frames(self._h, _d(t), _d(d)))
+
+    def set_prior(self, mu_DVR, Cov_DVR, mu_R1, Cov_R1):
+        a = [np.ascontiguousarray(x, np.float64) for x in (mu_DVR, Cov_DVR, mu_R1, Cov_R1)]
+        if a[0].shape != (N_ROI,) or a[1].shape != (N_ROI, N_ROI) or a[2].shape != (N_ROI,) or a[3].shape != (N_ROI, N_ROI):
+            raise ValueError("prior must be 48-dimensional")
+        self._ck(_lib.lib.petmh_set_prior(self._h, _d(a[0]), _d(a[1]), _d(a[2]), _d(a[3])))
+
+    def set_data(self, y_obs, tac_ref, k2p, sigma_noise=None):
+        """y_obs (S,48,54) = tac_noisy/dt; tac_ref (S,54); k2p (S,); sigma_noise (48,54).
+        float32 inputs take the bulk path (no conversion copy)."""
+        y = np.asarray(y_obs)
+        if y.ndim == 2:
+            y = y[None]
+        S = y.shape[0]
+        if y.shape[1:] != (N_ROI, N_FRAMES):
+            raise ValueError("y_obs must have shape (S,48,54)")
+        if y.dtype == np.float32:
+            y = np.ascontiguousarray(y)
+            cr = np.ascontiguousarray(np.asarray(tac_ref, np.float32).reshape(S, N_FRAMES))
+            k = np.ascontiguousarray(np.broadcast_to(np.asarray(k2p, np.float32).reshape(-1), (S,)))
+            sn = None if sigma_noise is None else np.ascontiguousarray(sigma_noise, np.float32)
+            self._ck(_lib.lib.petmh_set_data_f32(self._h, S, _f(y), _f(cr), _f(k), None if sn is None else _f(sn)))
+        else:
+            y = np.ascontiguousarray(y, np.float64)
+            cr = np.ascontiguousarray(np.asarray(tac_ref, np.float64).reshape(S, N_FRAMES))
+            k = np.ascontiguousarray(np.broadcast_to(np.asarray(k2p, np.float64).reshape(-1), (S,)))
+            sn = None if sigma_noise is None else np.ascontiguousarray(sigma_noise, np.float64)
+            self._ck(_lib.lib.petmh_set_data(self._h, S, _d(y), _d(cr), _d(k), None if sn is None else _d(sn)))
+        self.n_tac = S
+
+    # -- parity hooks ---------------------------------------------------------------------
+    def forward(self, tac, DVR, R1):
+        """(48,54) model TAC, == SRTM2.create_activity_curve(DVR,R1,k2p).T (mcmc.py:38-39)."""
+        a = np.ascontiguousarray(DVR, np.float64)
+        b = np.ascontiguousarray(R1, np.float64)
+        out = np.empty((N_ROI, N_FRAMES), np.float64)
+        self._ck(_lib.lib.petmh_forward(self._h, int(tac), _d(a), _d(b), _d(out)))
+        return out
+
+    def loglik(self, tac, DVR, R1):
+        """(ll per ROI (48,), (logprior_DVR, logprior_R1)) of the pymc model (mcmc.py:148-155)."""
+        a = np.ascontiguousarray(DVR, np.float64)
+        b = np.ascontiguousarray(R1, np.float64)
+        ll = np.empty(N_ROI, np.float64)
+        lp = np.empty(2, np.float64)
+        self._ck(_lib.lib.petmh_loglik(self._h, int(tac), _d(a), _d(b), _d(ll), _d(lp)))
+        return ll, lp
+
+    def operator(self, tac):
+        m = np.empty((N_FRAMES, N_FRAMES), np.float64)
+        self._ck(_lib.lib.petmh_get_operator(self._h, int(tac), _d(m)))
+        return m
+
+    def philox_raw(self, chain_gid, sweep, block):
+        out = np.empty((N_ROI, 4), np.uint32)
+        self._ck(_lib.lib.petmh_philox_raw(self._h, int(chain_gid), int(sweep), int(block),
+                                           out.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return out
+
+    # -- sampling ---------------------------------------------------------------------------
+    def run(self, draws, tune, thin=1):
+        self._ck(_lib.lib.petmh_run(self._h, int(draws), int(tune), int(thin)))
+
+    def reset(self):
+        self._ck(_lib.lib.petmh_reset(self._h))
+
+    def plan(self, draws, tune, thin=1):
+        self._ck(_lib.lib.petmh_plan(self._h, int(draws), int(tune), int(thin)))
+
+    def advance(self, n_sweeps):
+        self._ck(_lib.lib.petmh_advance(self._h, int(n_sweeps)))
+
+    def run_taped(self, tac, normals, logu, rank, tune):
+        """normals/logu (c,s,2,48) f32, rank (c,s,2,48) u8 -> dict(draws, delta, accept, scale)."""
+        n = np.ascontiguousarray(normals, np.float32)
+        lu = np.ascontiguousarray(logu, np.float32)
+        rk = np.ascontiguousarray(rank, np.uint8)
+        c, s = n.shape[:2]
+        draws = np.empty((c, s, 2, N_ROI), np.float32)
+        delta = np.empty((c, s, 2, N_ROI), np.float32)
+        acc = np.empty((c, s, 2, N_ROI), np.uint8)
+        scale = np.empty((c, 2, N_ROI), np.float32)
+        u8 = C.POINTER(C.c_uint8)
+        self._ck(_lib.lib.petmh_run_taped(self._h, int(tac), c, s, int(tune), _f(n), _f(lu), rk.ctypes.data_as(u8),
+                                          _f(draws), _f(delta), acc.ctypes.data_as(u8), _f(scale)))
+        return dict(draws=draws, delta=delta, accept=acc.astype(bool), scale=scale)
+
+    # -- outputs ------------------------------------------------------------------------------
+    @property
+    def n_stored(self):
+        return _lib.lib.petmh_n_stored(self._h)
+
+    def chains(self):
+        """(DVR_mcmc, R1_mcmc), each (S, chains, n_stored, 48) float32 (mcmc.py:162-163 layout per TAC)."""
+        ns = self.n_stored
+        shape = (self.n_tac, self.n_chains, ns, N_ROI)
+        dvr = np.empty(shape, np.float32)
+        r1 = np.empty(shape, np.float32)
+        self._ck(_lib.lib.petmh_get_chains(self._h, _f(dvr), _f(r1)))
+        return dvr, r1
+
+    def summary(self):
+        """(S, 96, 8) float32; columns _lib.STAT_NAMES; rows DVR[0..47] then R1[0..47]."""
+        out = np.empty((self.n_tac, N_COORD, N_STATS), np.float32)
+        self._ck(_lib.lib.petmh_get_summary(self._h, _f(out)))
+        return out
+
+    def summary_into(self, device_ptr, stream=None):
+        """Write the (S,96,8) f32 summary to DEVICE memory (e.g. an all-gather slot)."""
+        self._ck(_lib.lib.petmh_summary_device(self._h, C.c_void_p(int(device_ptr)),
+                                               C.c_void_p(int(stream)) if stream else None))
+
+    def state(self):
+        q = np.empty((self.n_tac, self.n_chains, N_COORD), np.float32)
+        sc = np.empty_like(q)
+        self._ck(_lib.lib.petmh_get_state(self._h, _f(q), _f(sc)))
+        return q, sc
+
+    def set_stream(self, stream):
+        self._ck(_lib.lib.petmh_set_stream(self._h, C.c_void_p(int(stream))))
+
+    def synchronize(self):
+        self._ck(_lib.lib.petmh_synchronize(self._h))
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        n = C.c_int()
+        self._ck(_lib.lib.petmh_last_kernel_ms(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
