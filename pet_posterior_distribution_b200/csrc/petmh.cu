@@ -55,6 +55,7 @@ struct petmh_handle {
     float last_ms = 0.f;
     int last_launches = 0;
     int launch_sweeps = 200;
+    int variant = 0;
 };
 
 static int fail(petmh_t* h, int code, const char* fmt, ...) {
@@ -197,6 +198,7 @@ extern "C" int petmh_create(const petmh_cfg* cfg, petmh_t** out) {
     h = new petmh_handle();
     h->cfg = *cfg;
     if (const char* e = getenv("PETMH_LAUNCH_SWEEPS")) h->launch_sweeps = std::max(1, atoi(e));
+    if (const char* e = getenv("PETMH_VARIANT")) h->variant = atoi(e) == 1 ? 1 : 0;
     auto bail = [&](int code) { petmh_destroy(h); return code; };
 #define CUC(call)                                                                                     \
     do {                                                                                              \
@@ -228,7 +230,8 @@ extern "C" int petmh_create(const petmh_cfg* cfg, petmh_t** out) {
     if (cfg->max_draws > 0) CUC(cudaMalloc(&h->d_draws, NC * (size_t)cfg->max_draws * 96 * sizeof(float)));
     CUC(cudaMalloc(&h->d_scratch, (48 * NT + 256) * sizeof(float)));
     CUC(cudaMalloc(&h->d_scratch64, NT * NT * sizeof(double)));
-    CUC(cudaFuncSetAttribute(mh_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(256)));
+    CUC(cudaFuncSetAttribute(mh_sweep_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(256)));
+    CUC(cudaFuncSetAttribute(mh_sweep_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(128)));
     CUC(cudaFuncSetAttribute(forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_MOM + 32 * SLOTS * NT * 4));
 #undef CUC
     *out = h;
@@ -515,7 +518,7 @@ extern "C" int petmh_plan(petmh_t* h, int draws, int tune, int thin) {
 static int threads_per_cta(const petmh_t* h) {
     int t = h->cfg.n_chains * 16;
     t = (t + 31) / 32 * 32;
-    return std::min(t, 256);
+    return std::min(t, h->variant == 0 ? 256 : 128);
 }
 
 extern "C" int petmh_advance(petmh_t* h, int n_sweeps) {
@@ -545,7 +548,8 @@ extern "C" int petmh_advance(petmh_t* h, int n_sweeps) {
         const int half = (drawing && h->sweep >= half_at) ? 1 : 0;
         p.mom_half = half;
         p.mom_n_before = h->mom_n[half];
-        mh_sweep_kernel<<<grid, nthr, smem_bytes(nthr), h->stream>>>(p);
+        if (h->variant == 0) mh_sweep_kernel<0><<<grid, nthr, smem_bytes(nthr), h->stream>>>(p);
+        else mh_sweep_kernel<1><<<grid, nthr, smem_bytes(nthr), h->stream>>>(p);
         CU(cudaGetLastError());
         if (drawing) { h->mom_n[half] += n; h->mom_launches[half] += 1; }
         h->sweep += n;
@@ -599,7 +603,8 @@ extern "C" int petmh_run_taped(petmh_t* h, int tac, int n_tape_chains, int n_swe
     int nthr = std::min(256, (n_tape_chains * 16 + 31) / 32 * 32);
     const int cpc = nthr / 16;
     const unsigned grid = (unsigned)((n_tape_chains + cpc - 1) / cpc);
-    mh_sweep_kernel<<<grid, nthr, smem_bytes(nthr), h->stream>>>(p);
+    if (h->variant == 0) mh_sweep_kernel<0><<<grid, nthr, smem_bytes(nthr), h->stream>>>(p);
+    else { nthr = std::min(nthr, 128); mh_sweep_kernel<1><<<(unsigned)((n_tape_chains + nthr / 16 - 1) / (nthr / 16)), nthr, smem_bytes(nthr), h->stream>>>(p); }
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(draws_out, dd, n * 4, cudaMemcpyDeviceToHost, h->stream));
     if (delta_out) CU(cudaMemcpyAsync(delta_out, ddelta, n * 4, cudaMemcpyDeviceToHost, h->stream));

@@ -25,7 +25,6 @@ namespace petmh {
 
 constexpr int NROI = 48;
 constexpr int NT = PETMH_T;          // 54 frames
-constexpr int NTP = PETMH_TPAD;      // 56
 constexpr int YS = 60;               // padded row stride (floats) of per-ROI frame arrays in smem
 constexpr int NCOL = PETMH_NCOL;     // 45 active columns of M
 constexpr int NGRID = 2 * NT;        // 108 resample points (kinetic_model.py:14)
@@ -33,10 +32,11 @@ constexpr int MPACK = PETMH_MPACK;
 constexpr int SLOTS = 3;             // ROIs per lane
 constexpr int TUNE_INTERVAL = 100;   // pymc Metropolis tune_interval
 constexpr float Z_CUT = 3.85f;       // erfc(z)/2 < 2^-25 beyond: (1 - h) rounds to 1 in fp32
-constexpr int RB0 = PETMH_ROWBLOCK0, RB1 = PETMH_ROWBLOCK1, RB2 = PETMH_ROWBLOCK2;
-constexpr int NPAIR = (RB1 - RB0) / 2;  // accumulator pairs per row block (both blocks equal)
-static_assert(RB2 - RB1 == RB1 - RB0, "row blocks must have equal size");
-static_assert(PETMH_NBLOCKS == 2, "kernel written for two row blocks");
+constexpr int RB = PETMH_RB;          // 18 rows per row block
+constexpr int NBLK = PETMH_NBLK;      // 3 row blocks
+constexpr int RSTRIDE = PETMH_RSTRIDE;// 20 floats per packed column of a block
+constexpr int NPAIR = RB / 2;         // 9 accumulator pairs per item
+static_assert(RB == 18 && NBLK == 3 && RSTRIDE == 20 && YS == NBLK * RSTRIDE, "eval3 is written for 3 blocks of 18 rows");
 
 // Frame-grid-only tables (host-built in fp64, see petmh.cu build_frame_tables):
 // W_fwd / W_back of SURVEY.md A.2 in sparse two-tap form.
@@ -163,9 +163,7 @@ __device__ __forceinline__ float half_erfc(float z) {
 // ------------------------------------------------------------------------------------
 // Per-TAC shared-memory image (byte offsets into dynamic shared memory, all 16B aligned)
 // ------------------------------------------------------------------------------------
-constexpr int SM_P = 0;                                   // double [2][48][48]
-constexpr int SM_MU = SM_P + 2 * 48 * 48 * 8;             // double [2][48]
-constexpr int SM_CRS = SM_MU + 2 * 48 * 8;                // double [NGRID]
+constexpr int SM_CRS = 0;                                 // double [NGRID]
 constexpr int SM_M = SM_CRS + NGRID * 8;                  // float [MPACK]   packed operator
 constexpr int SM_CR = SM_M + MPACK * 4;                   // float [64]      reference TAC, [60] = k2p
 constexpr int SM_YCC = SM_CR + 64 * 4;                    // float [48][YS]  y * cc
@@ -184,148 +182,151 @@ constexpr int K2P_SLOT = 60;
 // is only non-null in the parity hook.
 // ------------------------------------------------------------------------------------
 constexpr int K = SLOTS;
+
+// one frame of one item: TAC assembly, clamp, Gaussian term, z for the truncation term
+#define PETMH_FRAME(conv_, cr_, cc_, yc_, s_, z_)                                            \
+    {                                                                                        \
+        float sv_ = fmaf(coef0, (conv_), r10 * (cr_));   /* kinetic_model.py:157-158 */      \
+        sv_ = sv_ < 0.f ? 1e-6f : sv_;                   /* mcmc.py:152 */                   \
+        const float rs_ = rsqrt_approx(sv_);                                                 \
+        const float uu_ = fmaf(-sv_, (cc_), (yc_)) * rs_; /* (y - s) / (sig sqrt(2 s)) */    \
+        G0 = fmaf(uu_, uu_, G0);                         /* (y-s)^2 / (2 s sig^2) */         \
+        (s_) = sv_;                                                                          \
+        (z_) = sv_ * rs_ * (cc_);                        /* sqrt(s) / (sig sqrt2) */         \
+    }
+
+// log2 of prod_t s_t (1 - erfc(z_t)/2)^2 over up to 4 frames; the erfc factor is skipped
+// warp-uniformly when every lane's z >= Z_CUT (its value never depends on neighbours)
+template <int N>
+__device__ __forceinline__ float trunc_log2(const float (&sv)[4], const float (&zv)[4]) {
+    float zmin = zv[0];
+#pragma unroll
+    for (int u = 1; u < N; u++) zmin = fminf(zmin, zv[u]);
+    float pr = sv[0];
+    if (__any_sync(0xffffffffu, !(zmin >= Z_CUT))) {   // NaN -> evaluate
+        pr = 1.f;
+#pragma unroll
+        for (int u = 0; u < N; u++) {
+            const float gsel = (zv[u] >= Z_CUT) ? 1.f : (1.f - half_erfc(zv[u]));
+            pr *= sv[u] * gsel * gsel;
+        }
+    } else {
+#pragma unroll
+        for (int u = 1; u < N; u++) pr *= sv[u];
+    }
+    return lg2_approx(pr);
+}
+
+template <int VARIANT>
 __device__ __noinline__ float3 eval3(const int l16, const float d0, const float d1, const float d2, const float a0,
                                      const float a1, const float a2, float* tac_out) {
     extern __shared__ __align__(16) unsigned char smem[];
     const float* sM = reinterpret_cast<const float*>(smem + SM_M);
-    const float4* cr4 = reinterpret_cast<const float4*>(smem + SM_CR);
-    const float4* ycc4 = reinterpret_cast<const float4*>(smem + SM_YCC) + l16 * (YS / 4);
-    const float4* cc4 = reinterpret_cast<const float4*>(smem + SM_CC) + l16 * (YS / 4);
-    const float k2p = reinterpret_cast<const float*>(smem + SM_CR)[K2P_SLOT];
-    const float dvr[K] = {d0, d1, d2}, r1[K] = {a0, a1, a2};
-    float na[K], coef[K], G[K], S[K];
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        const float k2 = k2p * r1[k];              // kinetic_model.py:153
-        const float k2a = k2 / dvr[k];             // :154
-        coef[k] = fmaf(-r1[k], k2a, k2);           // (k2 - R1*k2a), :157
-        na[k] = k2a * -1.4426950408889634f;        // exp(-k2a t) = 2^(na t)
-        G[k] = 0.f;
-        S[k] = 0.f;
+    const float* sCr = reinterpret_cast<const float*>(smem + SM_CR);
+    const float k2p = sCr[K2P_SLOT];
+    // rotating per-item registers: slot 0 is the item being processed by the likelihood loop
+    float na0, na1, na2, coef0, coef1, coef2, r10 = a0, r11 = a1, r12 = a2;
+    float G0 = 0.f, G1 = 0.f, G2 = 0.f, S0 = 0.f, S1 = 0.f, S2 = 0.f;
+    {
+        const float k20 = k2p * a0, k21 = k2p * a1, k22 = k2p * a2;   // kinetic_model.py:153
+        const float k2a0 = k20 / d0, k2a1 = k21 / d1, k2a2 = k22 / d2; // :154
+        coef0 = fmaf(-a0, k2a0, k20);                                   // (k2 - R1*k2a), :157
+        coef1 = fmaf(-a1, k2a1, k21);
+        coef2 = fmaf(-a2, k2a2, k22);
+        na0 = k2a0 * -1.4426950408889634f;                              // exp(-k2a t) = 2^(na t)
+        na1 = k2a1 * -1.4426950408889634f;
+        na2 = k2a2 * -1.4426950408889634f;
     }
+    int rowoff0 = l16 * YS, rowoff1 = (l16 + 16) * YS, rowoff2 = (l16 + 32) * YS;   // ROI rows of ycc / cc
+    const float* sYcc = reinterpret_cast<const float*>(smem + SM_YCC);
+    const float* sCc = reinterpret_cast<const float*>(smem + SM_CC);
 
-#define PETMH_ECOL(ci)                                               \
-    {                                                                \
-        _Pragma("unroll") for (int k = 0; k < K; k++) {              \
-            const float e_ = ex2_approx(na[k] * c_tcol[ci]);         \
-            ed[k] = pack2(e_, e_);                                   \
-        }                                                            \
+#pragma unroll 1
+    for (int blk = 0; blk < NBLK; blk++) {
+        const int ncols = blk == 0 ? 11 : (blk == 1 ? 28 : 45);         // PETMH_NCB
+        const float4* Mp = reinterpret_cast<const float4*>(sM + (blk == 0 ? 0 : (blk == 1 ? 220 : 780)));   // PETMH_MOFF
+        u64 acc0[NPAIR], acc1[NPAIR], acc2[NPAIR];
+#pragma unroll
+        for (int p = 0; p < NPAIR; p++) acc0[p] = acc1[p] = acc2[p] = 0ull;
+        // ---- conv rows of this block: acc += M[:, c] * e_c over the block's active columns ----
+        // software pipeline: the next column's 5 chunks are in flight while this one is consumed
+        float4 mc0 = Mp[0], mc1 = Mp[1], mc2 = Mp[2], mc3 = Mp[3];
+        float2 mc4 = *reinterpret_cast<const float2*>(Mp + 4);
+#pragma unroll 2
+        for (int c = 0; c < ncols; c++) {
+            Mp += RSTRIDE / 4;   // (the read past the last column stays inside shared memory)
+            const float4 mn0 = Mp[0], mn1 = Mp[1], mn2 = Mp[2], mn3 = Mp[3];
+            const float2 mn4 = *reinterpret_cast<const float2*>(Mp + 4);
+            const float tc = c_tcol[c];
+            const float e0 = ex2_approx(na0 * tc), e1 = ex2_approx(na1 * tc), e2 = ex2_approx(na2 * tc);
+            const u64 ed0 = pack2(e0, e0), ed1 = pack2(e1, e1), ed2 = pack2(e2, e2);   // FFMA2 scalar-broadcast operand
+#define PETMH_CH(v, m)                                                                                          \
+    {                                                                                                           \
+        const u64 m01 = pack2(m.x, m.y), m23 = pack2(m.z, m.w);                                                 \
+        ffma2(acc0[2 * v], m01, ed0); ffma2(acc1[2 * v], m01, ed1); ffma2(acc2[2 * v], m01, ed2);               \
+        ffma2(acc0[2 * v + 1], m23, ed0); ffma2(acc1[2 * v + 1], m23, ed1); ffma2(acc2[2 * v + 1], m23, ed2);   \
     }
-#define PETMH_MQ(off, p)                                                              \
-    {                                                                                 \
-        const float4 m_ = *reinterpret_cast<const float4*>(sM + (off));               \
-        const u64 m01_ = pack2(m_.x, m_.y), m23_ = pack2(m_.z, m_.w);                 \
-        _Pragma("unroll") for (int k = 0; k < K; k++) {                               \
-            ffma2(acc[k][p], m01_, ed[k]);                                            \
-            ffma2(acc[k][(p) + 1], m23_, ed[k]);                                      \
-        }                                                                             \
-    }
-#define PETMH_MP(off, p)                                                              \
-    {                                                                                 \
-        const float2 m_ = *reinterpret_cast<const float2*>(sM + (off));               \
-        const u64 m01_ = pack2(m_.x, m_.y);                                           \
-        _Pragma("unroll") for (int k = 0; k < K; k++) ffma2(acc[k][p], m01_, ed[k]);  \
-    }
-
-#pragma unroll
-    for (int blk = 0; blk < 2; blk++) {
-        u64 acc[K][NPAIR];
-        u64 ed[K];
-#pragma unroll
-        for (int k = 0; k < K; k++)
-#pragma unroll
-            for (int p = 0; p < NPAIR; p++) acc[k][p] = 0ull;
-        if (blk == 0) {
-            PETMH_ME_BLOCK0(PETMH_ECOL, PETMH_MQ, PETMH_MP)
-        } else {
-            PETMH_ME_BLOCK1(PETMH_ECOL, PETMH_MQ, PETMH_MP)
-        }
-        const int b0 = blk == 0 ? RB0 : RB1;
-        const int b1 = blk == 0 ? RB1 : RB2;
-        // likelihood for frames b0 .. min(b1, NT)-1 in aligned groups of 4
-#pragma unroll
-        for (int g = b0 / 4; g < b1 / 4; g++) {
-            const float4 crv = cr4[g];
-            const float crj[4] = {crv.x, crv.y, crv.z, crv.w};
-            float zz[K][4], ss[K][4];
-            float zmin = 1e30f;
-#pragma unroll
-            for (int k = 0; k < K; k++) {
-                const float4 yv = ycc4[k * 16 * (YS / 4) + g];
-                const float4 cv = cc4[k * 16 * (YS / 4) + g];
-                const float yj[4] = {yv.x, yv.y, yv.z, yv.w};
-                const float cj[4] = {cv.x, cv.y, cv.z, cv.w};
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int j = 4 * g + u;
-                    if (j < NT) {
-                        float lo, hi;
-                        unpack2(acc[k][(j - b0) >> 1], lo, hi);
-                        const float conv = (j & 1) ? hi : lo;
-                        float s = fmaf(coef[k], conv, r1[k] * crj[u]);   // kinetic_model.py:157-158
-                        s = s < 0.f ? 1e-6f : s;                          // mcmc.py:152
-                        const float rs = rsqrt_approx(s);
-                        const float w = fmaf(-s, cj[u], yj[u]);           // (y - s) / (sig sqrt2)
-                        const float uu = w * rs;
-                        G[k] = fmaf(uu, uu, G[k]);                        // (y-s)^2 / (2 s sig^2)
-                        const float z = s * rs * cj[u];                   // sqrt(s) / (sig sqrt2)
-                        zz[k][u] = z;
-                        ss[k][u] = s;
-                        zmin = fminf(zmin, z);
-                    } else {
-                        zz[k][u] = 1e30f;
-                        ss[k][u] = 1.f;
-                    }
-                }
+            PETMH_CH(0, mc0) PETMH_CH(1, mc1) PETMH_CH(2, mc2) PETMH_CH(3, mc3)
+#undef PETMH_CH
+            {
+                const u64 m01 = pack2(mc4.x, mc4.y);
+                ffma2(acc0[8], m01, ed0); ffma2(acc1[8], m01, ed1); ffma2(acc2[8], m01, ed2);
             }
+            mc0 = mn0; mc1 = mn1; mc2 = mn2; mc3 = mn3; mc4 = mn4;
+        }
+        // ---- likelihood of the block's 18 frames, one item per iteration (registers rotate) ----
+        const float* crb = sCr + blk * RB;
+#pragma unroll 1
+        for (int it = 0; it < K; it++) {
+            const float4* y4 = reinterpret_cast<const float4*>(sYcc + rowoff0 + blk * RSTRIDE);
+            const float4* c4 = reinterpret_cast<const float4*>(sCc + rowoff0 + blk * RSTRIDE);
+            float cv[RSTRIDE], yv[RSTRIDE], conv[RB];
+#pragma unroll
+            for (int v = 0; v < RSTRIDE / 4; v++) {
+                const float4 a = c4[v], b = y4[v];
+                cv[4 * v] = a.x; cv[4 * v + 1] = a.y; cv[4 * v + 2] = a.z; cv[4 * v + 3] = a.w;
+                yv[4 * v] = b.x; yv[4 * v + 1] = b.y; yv[4 * v + 2] = b.z; yv[4 * v + 3] = b.w;
+            }
+#pragma unroll
+            for (int p = 0; p < NPAIR; p++) unpack2(acc0[p], conv[2 * p], conv[2 * p + 1]);
             if (tac_out != nullptr) {   // parity hook only (warp-uniform): the unclamped TAC
 #pragma unroll
-                for (int k = 0; k < K; k++)
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int j = 4 * g + u;
-                        if (j < NT) {
-                            float lo, hi;
-                            unpack2(acc[k][(j - b0) >> 1], lo, hi);
-                            tac_out[k * NT + j] = fmaf(coef[k], (j & 1) ? hi : lo, r1[k] * crj[u]);
-                        }
-                    }
+                for (int u = 0; u < RB; u++) tac_out[it * NT + blk * RB + u] = fmaf(coef0, conv[u], r10 * crb[u]);
             }
-            // truncation term -log(1 - erfc(z)/2): skipped (warp-uniformly) when every
-            // lane's z >= Z_CUT; the value itself never depends on the neighbours.
-            const bool need = !(zmin >= Z_CUT);   // NaN -> need
-            if (__any_sync(0xffffffffu, need)) {
 #pragma unroll
-                for (int k = 0; k < K; k++) {
-                    float pr = 1.f;
+            for (int g = 0; g < 4; g++) {
+                float sv[4], zv[4];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const float z = zz[k][u];
-                        const float gsel = (z >= Z_CUT) ? 1.f : (1.f - half_erfc(z));
-                        pr *= ss[k][u] * gsel * gsel;
-                    }
-                    S[k] += lg2_approx(pr);
+                for (int u = 0; u < 4; u++) {
+                    const int f = 4 * g + u;
+                    PETMH_FRAME(conv[f], crb[f], cv[f], yv[f], sv[u], zv[u])
                 }
-            } else {
-#pragma unroll
-                for (int k = 0; k < K; k++) {
-                    const float pr = (ss[k][0] * ss[k][1]) * (ss[k][2] * ss[k][3]);
-                    S[k] += lg2_approx(pr);
-                }
+                S0 += trunc_log2<4>(sv, zv);
             }
+            {
+                float sv[4], zv[4];
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int f = 16 + u;
+                    PETMH_FRAME(conv[f], crb[f], cv[f], yv[f], sv[u], zv[u])
+                }
+                S0 += trunc_log2<2>(sv, zv);
+            }
+            // rotate item registers: (0,1,2) <- (1,2,0)
+#pragma unroll
+            for (int p = 0; p < NPAIR; p++) { const u64 t_ = acc0[p]; acc0[p] = acc1[p]; acc1[p] = acc2[p]; acc2[p] = t_; }
+            { const float t_ = coef0; coef0 = coef1; coef1 = coef2; coef2 = t_; }
+            { const float t_ = r10; r10 = r11; r11 = r12; r12 = t_; }
+            { const float t_ = G0; G0 = G1; G1 = G2; G2 = t_; }
+            { const float t_ = S0; S0 = S1; S1 = S2; S2 = t_; }
+            { const int t_ = rowoff0; rowoff0 = rowoff1; rowoff1 = rowoff2; rowoff2 = t_; }
         }
     }
-#undef PETMH_ECOL
-#undef PETMH_MQ
-#undef PETMH_MP
     const unsigned char* bad = smem + SM_BAD;
-    float out[K];
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        const float v = -G[k] - 0.34657359027997264f * S[k];   // -(ln 2)/2 * log2(prod)
-        out[k] = bad[l16 + 16 * k] ? -INFINITY : v;
-    }
-    return make_float3(out[0], out[1], out[2]);
+    const float v0 = -G0 - 0.34657359027997264f * S0;   // -(ln 2)/2 * log2(prod)
+    const float v1 = -G1 - 0.34657359027997264f * S1;
+    const float v2 = -G2 - 0.34657359027997264f * S2;
+    return make_float3(bad[l16] ? -INFINITY : v0, bad[l16 + 16] ? -INFINITY : v1, bad[l16 + 32] ? -INFINITY : v2);
 }
 
 // ------------------------------------------------------------------------------------
@@ -367,20 +368,13 @@ __device__ __forceinline__ void build_M_packed(const FrameTables* ft, const doub
     }
 }
 
-__device__ __forceinline__ void load_tac_image(const SweepParams& p, int tac, unsigned char* smem, int tid, int nthr,
-                                               bool with_prior) {
-    double* sP = reinterpret_cast<double*>(smem + SM_P);
-    double* sMu = reinterpret_cast<double*>(smem + SM_MU);
+__device__ __forceinline__ void load_tac_image(const SweepParams& p, int tac, unsigned char* smem, int tid, int nthr) {
     double* sCrs = reinterpret_cast<double*>(smem + SM_CRS);
     float* sM = reinterpret_cast<float*>(smem + SM_M);
     float* sCr = reinterpret_cast<float*>(smem + SM_CR);
     float* sYcc = reinterpret_cast<float*>(smem + SM_YCC);
     float* sCc = reinterpret_cast<float*>(smem + SM_CC);
     unsigned char* sBad = smem + SM_BAD;
-    if (with_prior) {
-        for (int i = tid; i < 2 * 48 * 48; i += nthr) sP[i] = p.P[i];
-        for (int i = tid; i < 2 * 48; i += nthr) sMu[i] = p.mu[i];
-    }
     const double* cref = p.cref + (size_t)tac * NT;
     build_crs(p.ft, cref, sCrs, tid, nthr);
     for (int i = tid; i < 64; i += nthr) sCr[i] = i < NT ? (float)cref[i] : (i == K2P_SLOT ? p.k2p[tac] : 0.f);
@@ -388,10 +382,12 @@ __device__ __forceinline__ void load_tac_image(const SweepParams& p, int tac, un
     __syncthreads();
     build_M_packed(p.ft, sCrs, sM, tid, nthr);
     const float* y = p.y + (size_t)tac * NROI * NT;
-    for (int i = tid; i < NROI * YS; i += nthr) {
-        const int r = i / YS, j = i - r * YS;
+    for (int i = tid; i < NROI * YS; i += nthr) {   // layout [roi][block][RSTRIDE], RB frames used
+        const int r = i / YS, w = i - r * YS;
+        const int blk = w / RSTRIDE, u = w - blk * RSTRIDE;
+        const int j = blk * RB + u;
         float c = 0.f, yc = 0.f;
-        if (j < NT) {
+        if (u < RB) {
             c = p.cc[r * NT + j];
             const float yv = y[r * NT + j];
             yc = yv * c;
@@ -417,7 +413,10 @@ __device__ __forceinline__ float tune_factor(int c) {
 // ------------------------------------------------------------------------------------
 // The fused sweep kernel.  blockDim.x = 32*NW; one CTA = 2*NW chains of one TAC.
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2) mh_sweep_kernel(const SweepParams p) {
+// VARIANT 0: 256-thread CTAs, 2 CTAs/SM (128-register cap, eval3 spills a little);
+// VARIANT 1: 128-thread CTAs, 3 CTAs/SM (168-register cap, no spills).
+template <int VARIANT>
+__global__ void __launch_bounds__(VARIANT == 0 ? 256 : 128, VARIANT == 0 ? 2 : 3) mh_sweep_kernel(const SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, nthr = blockDim.x;
     const bool TAPED = p.tape_n != nullptr;
@@ -434,9 +433,9 @@ __global__ void __launch_bounds__(256, 2) mh_sweep_kernel(const SweepParams p) {
     const unsigned long long gid = (p.tac_gid0 + (unsigned long long)tac) * (unsigned long long)p.n_chains +
                                    (unsigned long long)(active ? chain : 0);
 
-    load_tac_image(p, tac, smem, tid, nthr, true);
-    const double* sP = reinterpret_cast<const double*>(smem + SM_P);
-    const double* sMu = reinterpret_cast<const double*>(smem + SM_MU);
+    load_tac_image(p, tac, smem, tid, nthr);
+    const double* __restrict__ sP = p.P;     // [2][48][48] fp64, L1/L2 resident (37 KB)
+    const double* __restrict__ sMu = p.mu;
     double* sMom = reinterpret_cast<double*>(smem + SM_MOM);
 #pragma unroll
     for (int m = 0; m < 18; m++) sMom[m * nthr + tid] = 0.0;
@@ -482,7 +481,7 @@ __global__ void __launch_bounds__(256, 2) mh_sweep_kernel(const SweepParams p) {
     }
     float ll_old[SLOTS];
     {
-        const float3 v = eval3(l16, q[0][0], q[0][1], q[0][2], q[1][0], q[1][1], q[1][2], nullptr);
+        const float3 v = eval3<VARIANT>(l16, q[0][0], q[0][1], q[0][2], q[1][0], q[1][1], q[1][2], nullptr);
         ll_old[0] = v.x; ll_old[1] = v.y; ll_old[2] = v.z;
     }
     float prev[2][SLOTS];   // previous recorded draw (lag-1 products)
@@ -530,8 +529,8 @@ __global__ void __launch_bounds__(256, 2) mh_sweep_kernel(const SweepParams p) {
             for (int s = 0; s < SLOTS; s++) qn[s] = __fadd_rn(q[b][s], __fmul_rn(nrm[s], scale[b][s]));
             // ---- phase A ----
             {
-                const float3 v = b == 0 ? eval3(l16, qn[0], qn[1], qn[2], q[1][0], q[1][1], q[1][2], nullptr)
-                                        : eval3(l16, q[0][0], q[0][1], q[0][2], qn[0], qn[1], qn[2], nullptr);
+                const float3 v = b == 0 ? eval3<VARIANT>(l16, qn[0], qn[1], qn[2], q[1][0], q[1][1], q[1][2], nullptr)
+                                        : eval3<VARIANT>(l16, q[0][0], q[0][1], q[0][2], qn[0], qn[1], qn[2], nullptr);
                 ll_new[0] = v.x; ll_new[1] = v.y; ll_new[2] = v.z;
             }
             // ---- phase B: resolve visits in key order ----
@@ -672,7 +671,7 @@ __global__ void forward_kernel(const SweepParams p, int tac, const float* dvr, c
                                float* ll_out) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
-    load_tac_image(p, tac, smem, tid, blockDim.x, false);
+    load_tac_image(p, tac, smem, tid, blockDim.x);
     if (tid < 32) {
         const int l16 = tid & 15;
         int roi[SLOTS];
@@ -684,7 +683,7 @@ __global__ void forward_kernel(const SweepParams p, int tac, const float* dvr, c
             b[s] = r1[roi[s]];
         }
         float* scratch = reinterpret_cast<float*>(smem + SM_MOM) + tid * SLOTS * NT;
-        const float3 v = eval3(l16, a[0], a[1], a[2], b[0], b[1], b[2], scratch);
+        const float3 v = eval3<0>(l16, a[0], a[1], a[2], b[0], b[1], b[2], scratch);
         ll[0] = v.x; ll[1] = v.y; ll[2] = v.z;
         if (tid < 16) {
 #pragma unroll
