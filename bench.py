@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""Benchmark of the MH-MCMC (SRTM2) hot path.  Contract: see the task statement.
+
+  python bench.py [--gpus N --steps K --warmup W]            -> ONE JSON line (this repo's CUDA path)
+  python bench.py --impl reference [--steps K --warmup W]     -> ONE JSON line (CPU restatement of the
+                                                                  reference algorithm on the host cores)
+Metric: MH chain-steps/s (chain-step = one scalar coordinate Metropolis update = one proposal,
+one 54-frame SRTM2 forward model + truncated-normal log-likelihood, one accept/reject;
+one pymc draw = 96 chain-steps).  Workload: BASELINE.json configs[4] ("throughput scaling"),
+sharded by TAC: --tacs-per-gpu TACs x 16 chains x 48 ROIs per GPU (131072 TACs/GPU = the
+config's 1M TACs at 8 GPUs); a step = --sweeps sweeps of every chain in the draw phase
+(scales tuned beforehand), running split-half moments on, no draw storage.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_ALG = 3980.0      # algorithmic FP32 flops per chain-step
+SFU_ALG = 369.0        # algorithmic MUFU ops per chain-step
+N_CHAINS = 16
+
+
+# ----------------------------------------------------------------------------------------------
+def _clock_sampler(stop, out, gpu_index):
+    q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    try:
+        p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    except Exception:
+        return
+    def reader():
+        for line in p.stdout:
+            out.append(line.strip())
+    th = threading.Thread(target=reader, daemon=True)
+    th.start()
+    stop.wait()
+    p.terminate()
+
+
+def _summarise_clocks(lines):
+    sm, mx, reasons = [], 0, set()
+    for ln in lines:
+        f = [x.strip() for x in ln.split(",")]
+        if len(f) < 8:
+            continue
+        try:
+            sm.append(float(f[0])); mx = max(mx, float(f[1]))
+        except ValueError:
+            continue
+        for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+            if v.lower().startswith("active"):
+                reasons.add(name)
+    if not sm:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    busy = [v for v in sm if v > 0.5 * max(sm)] or sm
+    return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle's reference-faithful mode (two full 48-ROI model log-probabilities per
+# chain-step, each a resample-convolve-interpolate forward call: the work pymc's delta_logp +
+# CreateTAC_SRTM2.perform do), one chain per process on all host cores.
+# ----------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    seed, sweeps, mode = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    import numpy as _np
+    from oracle import mh
+    from oracle.logp import Model
+    g = os.path.join(ROOT, "tests", "golden")
+    pr = _np.load(os.path.join(g, "prior_stats_nROI48.npz"))
+    ds = _np.load(os.path.join(g, "dataset_s0.1.npz"))
+    k = seed % ds["varDVR"].shape[0]
+    y = ds["tac_noisy_sampled"][k] / ds["dt"][None, :]
+    m = Model(ds["time_vector"], ds["vartacref"][k], ds["vark2p"][k], y, ds["sigma_noise"],
+              pr["mu_DVR"], pr["Cov_DVR"], pr["mu_R1"], pr["Cov_R1"])
+    tape = mh.Tape.random(sweeps, _np.random.default_rng(seed))
+    t0 = time.perf_counter()
+    mh.run_chain(m, tape, sweeps, 0, mode=mode)
+    return time.perf_counter() - t0
+
+
+def cpu_rate(sweeps, mode="faithful", cores=None, pool=None):
+    """chain-steps/s of `cores` independent chains (one process each), `sweeps` sweeps each."""
+    import multiprocessing as mp
+    cores = cores or os.cpu_count()
+    own = pool is None
+    if own:
+        pool = mp.get_context("fork").Pool(cores)
+    t0 = time.perf_counter()
+    pool.map(_cpu_worker, [(1000 + i, sweeps, mode) for i in range(cores)])
+    dt = time.perf_counter() - t0
+    if own:
+        pool.close()
+    return cores * sweeps * 96 / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count()
+    sweeps = args.ref_sweeps
+    pool = mp.get_context("fork").Pool(cores)
+    for _ in range(args.warmup):
+        cpu_rate(1, args.ref_mode, cores, pool)
+    times = []
+    for _ in range(args.steps):
+        _, dt = cpu_rate(sweeps, args.ref_mode, cores, pool)
+        times.append(dt)
+    pool.close()
+    total = sum(times)
+    value = cores * sweeps * 96 * args.steps / total
+    line = {"impl": "reference", "metric": "MH chain-steps/sec (SRTM2 lik)", "value": value, "unit": "chain-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "CPU restatement of mcmc.py element-wise Metropolis (pymc semantics, two full-model "
+                                   "log-probs per chain-step through the resample-convolve-interpolate SRTM2 forward model) "
+                                   "on golden synthetic TACs, 48 ROIs, 1 chain per host core",
+                       "sample": "%d chains x %d sweeps x 96 chain-steps per step" % (cores, sweeps)},
+            "cpu_baseline": {"value": value, "unit": "chain-steps/s", "cores": cores, "kind": "port",
+                             "sample": "%d steps of %d chains x %d sweeps x 96 chain-steps (%s oracle mode; pymc/pytensor "
+                                       "absent, /root/reference is Python and does not travel)" % (args.steps, cores, sweeps, args.ref_mode)},
+            "e2e": {"value": value, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from pet_posterior_distribution_b200 import MHSampler
+    from pet_posterior_distribution_b200 import sample_sim_data as gen
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    S, C, SW = args.tacs_per_gpu, N_CHAINS, args.sweeps
+
+    # ---- synthetic inputs: n_base unique TACs from the restated generator, tiled to S -------
+    prior = gen.load_prior()
+    nb = min(args.base_tacs, S)
+    ds = gen.generate(prior, nb, 0.1, test_style=False, seed=1234 + rank, device=local)
+    t, dtv = ds["time_vector"], ds["dt"]
+    yb = (np.asarray(ds["tac_noisy_sampled"]) / dtv[None, None, :]).astype(np.float32)
+    cb = np.asarray(ds["vartacref"], np.float32)
+    idx = np.arange(S) % nb
+    y_pin = torch.empty((S, 48, 54), dtype=torch.float32, pin_memory=True)
+    c_pin = torch.empty((S, 54), dtype=torch.float32, pin_memory=True)
+    k_pin = torch.full((S,), float(prior["mu_k2p"]), dtype=torch.float32).pin_memory()
+    y_pin.numpy()[:] = yb[idx]
+    c_pin.numpy()[:] = cb[idx]
+    out_pin = torch.empty((S, 96, 8), dtype=torch.float32, pin_memory=True)
+    sig = np.ascontiguousarray(ds["sigma_noise"], np.float32)
+
+    s = MHSampler(n_chains=C, max_tacs=S, max_draws=0, seed=2026, device=local, tac_gid0=rank * S)
+    s.set_frames(t, dtv)
+    s.set_prior(prior["mu_DVR"], prior["Cov_DVR"], prior["mu_R1"], prior["Cov_R1"])
+    s.set_data(yb, cb, k_pin.numpy()[:nb], sig)          # base set only: tune it
+    TUNE = args.tune
+    s.run(draws=0, tune=TUNE)
+    q0, sc0 = s.state()                                    # (nb, C, 96) tuned positions / scalings
+    # full batch, warm-started from the tuned base chains (Philox streams differ per TAC gid)
+    s.set_data_ptr(S, y_pin.data_ptr(), c_pin.data_ptr(), k_pin.data_ptr(), None)
+    s.set_state(q0[idx], sc0[idx], sweep=TUNE)
+    s.plan(draws=10 ** 8, tune=TUNE, thin=1)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        s.advance(SW)
+    # ---- timed: K steps, inputs resident in HBM ------------------------------------------------
+    stop, clk = threading.Event(), []
+    th = threading.Thread(target=_clock_sampler, args=(stop, clk, local), daemon=True)
+    th.start()
+    time.sleep(0.3)
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms, launches = 0.0, 0
+    for _ in range(args.steps):
+        s.advance(SW)
+        ms, nl = s.last_kernel_ms()
+        dev_ms += ms
+        launches += nl
+    barrier()
+    wall = time.perf_counter() - t0
+    stop.set()
+    # ---- timed: the same steps end to end through the public API with HOST buffers --------
+    for _ in range(1):
+        s.set_data_ptr(S, y_pin.data_ptr(), c_pin.data_ptr(), k_pin.data_ptr(), None); s.advance(SW); s.summary_ptr(out_pin.data_ptr())
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        s.set_data_ptr(S, y_pin.data_ptr(), c_pin.data_ptr(), k_pin.data_ptr(), None)   # H2D of the step's inputs (pinned)
+        s.advance(SW)
+        s.summary_ptr(out_pin.data_ptr())                                                 # D2H of the step's result (pinned)
+    barrier()
+    e2e_wall = time.perf_counter() - t1
+    summ = out_pin.numpy()
+    ok = bool(np.isfinite(summ[..., 0]).all() and np.isfinite(summ[..., 1]).all())
+
+    tt = torch.tensor([dev_ms * 1e-3, wall, e2e_wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_s, wall_s, e2e_s = [float(v) for v in tt.cpu()]
+    steps_per_step = S * C * 96 * SW * world
+    value = steps_per_step * args.steps / wall_s
+    kern_rate_1gpu = S * C * 96 * SW * args.steps / dev_s           # per GPU, device-event time of the sweep kernel
+    e2e_value = steps_per_step * args.steps / e2e_s
+    if rank == 0:
+        clocks = _summarise_clocks(clk)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
+        # FP32 peak: 148 SMs x 128 lanes x 2 flop x SM clock under load (tools/ubench measured 67.4 TFLOP/s
+        # = 94 % of this at 1.9 GHz; MEASURED_PEAKS.json has no FP32 figure, so the nominal formula is used)
+        peak_fp32 = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        peak_sfu = 148 * 16 * sm_mhz * 1e6
+        ach = kern_rate_1gpu * FLOP_ALG / 1e12
+        cpu = None
+        try:   # CPU baseline in a clean child process (no CUDA context in the forked workers)
+            def child(mode, sweeps):
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                                    "--ref-sweeps", str(sweeps), "--ref-mode", mode], capture_output=True, text=True, timeout=600,
+                                   env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+                return json.loads(r.stdout.strip().splitlines()[-1])
+            jf = child("faithful", args.cpu_sweeps)
+            jl = child("lean", args.cpu_sweeps * 40)
+            cpu = {"value": jf["value"], "unit": "chain-steps/s", "cores": jf["cpu_baseline"]["cores"], "kind": "port",
+                   "sample": jf["cpu_baseline"]["sample"], "restructured_cpu_value": jl["value"],
+                   "restructured_cpu_note": "lean oracle (operator M, cached per-ROI log-lik, incremental prior), same cores"}
+        except Exception as e:          # pragma: no cover
+            cpu = {"value": None, "unit": "chain-steps/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
+        line = {
+            "metric": "MH chain-steps/sec (SRTM2 lik)", "value": value, "unit": "chain-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall_s / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic: %d unique SRTM2 TACs per rank from the restated sample_sim_data.py priors (sigma 0.1), tiled to %d" % (nb, S),
+            "config": {"workload": "BASELINE configs[4] throughput scaling, TAC-sharded: %d TACs/GPU x %d chains x 48 ROIs "
+                                   "(1M TACs at 8 GPUs); step = %d sweeps (x96 chain-steps) of every chain, draw phase after "
+                                   "%d tuning sweeps" % (S, C, SW, TUNE),
+                       "tacs_per_gpu": S, "chains_per_tac": C, "sweeps_per_step": SW, "chain_steps_per_step": steps_per_step,
+                       "l2_policy": "per-step working set (inputs+state %.1f GB) >> 126 MB L2" % ((S * 10588 + S * C * 3500) / 1e9),
+                       "sec_per_48roi_posterior_60000_sweeps_amortised": 60000 * 96 * C / (value / world) ,
+                       "summary_finite": ok},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "chain-steps/s", "h2d_bytes_per_step": int(S * (48 * 54 + 54 + 1) * 4) * world,
+                    "d2h_bytes_per_step": int(S * 96 * 8 * 4) * world,
+                    "note": "per step: petmh_set_data_f32 from pinned host buffers + petmh_advance + petmh_get_summary to pinned host"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "fp32", "achieved": ach, "peak": peak_fp32, "unit": "TFLOP/s", "frac": ach / peak_fp32,
+                         "traffic": None,
+                         "note": "dominant kernel mh_sweep_kernel (%.1f %% of the step by CUDA events on its stream); achieved = "
+                                 "3980 algorithmic FP32 flop/chain-step x per-GPU kernel rate; peak = 148 SM x 128 lanes x 2 x SM clock "
+                                 "under load (nominal formula: MEASURED_PEAKS.json has no FP32 figure)" % (100 * dev_s / wall_s),
+                         "sfu_frac": kern_rate_1gpu * SFU_ALG / peak_sfu,
+                         "kernel_chain_steps_per_s_per_gpu": kern_rate_1gpu},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--tacs-per-gpu", type=int, default=131072)
+    ap.add_argument("--base-tacs", type=int, default=1024)
+    ap.add_argument("--sweeps", type=int, default=25)
+    ap.add_argument("--tune", type=int, default=1500)
+    ap.add_argument("--cpu-sweeps", type=int, default=40)
+    ap.add_argument("--ref-sweeps", type=int, default=8)
+    ap.add_argument("--ref-mode", default="faithful", choices=["faithful", "lean"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

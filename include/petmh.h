@@ -122,6 +122,9 @@ int petmh_get_summary(petmh_t* h, float* out);
  * `stream` (a cudaStream_t, 0 = the handle's). */
 int petmh_summary_device(petmh_t* h, float* d_out, void* stream);
 int petmh_get_state(petmh_t* h, float* q /*[n_tac][n_chains][96]*/, float* scale /*same*/);
+/* Resume / warm start: overwrite every chain's position and scaling (either may be NULL),
+ * zero the tuning counters and the running moments, and set the sweep counter. */
+int petmh_set_state(petmh_t* h, const float* q, const float* scale, int sweep);
 
 /* ---- timing / stream ------------------------------------------------------------- */
 int petmh_set_stream(petmh_t* h, void* cuda_stream);

@@ -656,6 +656,24 @@ extern "C" int petmh_get_state(petmh_t* h, float* q, float* scale) {
     return PETMH_OK;
 }
 
+extern "C" int petmh_set_state(petmh_t* h, const float* q, const float* scale, int sweep) {
+    if (!h || sweep < 0) return fail(h, PETMH_EINVAL, "bad argument");
+    if (h->n_tac < 1) return fail(h, PETMH_EINVAL, "petmh_set_data not called");
+    CU(cudaSetDevice(h->cfg.device));
+    const size_t NCall = (size_t)h->cfg.max_tacs * h->cfg.n_chains;
+    const size_t n = (size_t)h->n_tac * h->cfg.n_chains * 96;
+    if (q) CU(cudaMemcpyAsync(h->d_q, q, n * 4, cudaMemcpyHostToDevice, h->stream));
+    if (scale) CU(cudaMemcpyAsync(h->d_scale, scale, n * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemsetAsync(h->d_cnt, 0, NCall * 96, h->stream));
+    CU(cudaMemsetAsync(h->d_nacc, 0, NCall * 96 * sizeof(uint32_t), h->stream));
+    CU(cudaMemsetAsync(h->d_mom, 0, NCall * 96 * 6 * sizeof(float), h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->sweep = sweep;
+    h->mom_n[0] = h->mom_n[1] = 0;
+    h->mom_launches[0] = h->mom_launches[1] = 0;
+    return PETMH_OK;
+}
+
 extern "C" int petmh_summary_device(petmh_t* h, float* d_out, void* stream) {
     int rc = check_ready(h);
     if (rc) return rc;

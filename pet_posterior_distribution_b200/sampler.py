@@ -95,6 +95,17 @@ class MHSampler:
             self._ck(_lib.lib.petmh_set_data(self._h, S, _d(y), _d(cr), _d(k), None if sn is None else _d(sn)))
         self.n_tac = S
 
+    def set_data_ptr(self, n_tac, y_ptr, tac_ref_ptr, k2p_ptr, sigma_ptr=None):
+        """Bulk float32 path from raw HOST pointers (e.g. pinned torch tensors' data_ptr())."""
+        fp = C.POINTER(C.c_float)
+        cast = lambda p: C.cast(C.c_void_p(int(p)), fp) if p else None
+        self._ck(_lib.lib.petmh_set_data_f32(self._h, int(n_tac), cast(y_ptr), cast(tac_ref_ptr), cast(k2p_ptr), cast(sigma_ptr)))
+        self.n_tac = int(n_tac)
+
+    def summary_ptr(self, out_ptr):
+        """Summary (S,96,8) f32 into a raw HOST pointer (e.g. pinned memory)."""
+        self._ck(_lib.lib.petmh_get_summary(self._h, C.cast(C.c_void_p(int(out_ptr)), C.POINTER(C.c_float))))
+
     # -- parity hooks ---------------------------------------------------------------------
     def forward(self, tac, DVR, R1):
         """(48,54) model TAC, == SRTM2.create_activity_curve(DVR,R1,k2p).T (mcmc.py:38-39)."""
@@ -182,6 +193,15 @@ class MHSampler:
         sc = np.empty_like(q)
         self._ck(_lib.lib.petmh_get_state(self._h, _f(q), _f(sc)))
         return q, sc
+
+    def set_state(self, q=None, scale=None, sweep=0):
+        """Warm start / resume: (S, chains, 96) float32 positions and scalings."""
+        qq = None if q is None else np.ascontiguousarray(q, np.float32)
+        ss = None if scale is None else np.ascontiguousarray(scale, np.float32)
+        for a in (qq, ss):
+            if a is not None and a.shape != (self.n_tac, self.n_chains, N_COORD):
+                raise ValueError("state arrays must have shape (n_tac, n_chains, 96)")
+        self._ck(_lib.lib.petmh_set_state(self._h, None if qq is None else _f(qq), None if ss is None else _f(ss), int(sweep)))
 
     def set_stream(self, stream):
         self._ck(_lib.lib.petmh_set_stream(self._h, C.c_void_p(int(stream))))
