@@ -11,6 +11,7 @@
 #include "../../include/petmh.h"
 #include "petmh_device.cuh"
 #include "petmh_diag.cuh"
+#include "petmh_rankdiag.cuh"
 
 using namespace petmh;
 
@@ -696,6 +697,14 @@ extern "C" int petmh_summary_device(petmh_t* h, float* d_out, void* stream) {
     dp.lag_terms[0] = h->mom_n[0] - h->mom_launches[0];
     dp.lag_terms[1] = h->mom_n[1] - h->mom_launches[1];
     dp.out = d_out;
+    if (h->d_draws && dp.n_stored >= 8) {
+        // stored draws: rank-normalised split R-hat, bulk/tail ESS, MCSE (ArviZ semantics)
+        const int draw_sweeps = std::max(0, std::min(h->sweep, h->plan_tune + h->plan_draws) - h->plan_tune);
+        rc = launch_rank_summary(h->d_draws, h->n_tac, h->cfg.n_chains, h->cfg.max_draws, dp.n_stored, h->d_nacc, h->d_scale,
+                                 draw_sweeps, d_out, st);
+        if (rc) return fail(h, PETMH_ECUDA, "rank-diagnostics failed: %s", cudaGetErrorString((cudaError_t)rc));
+        return PETMH_OK;
+    }
     rc = launch_summary(dp, st);
     if (rc) return fail(h, PETMH_ECUDA, "summary kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
     return PETMH_OK;

@@ -169,8 +169,8 @@ constexpr int SM_CR = SM_M + MPACK * 4;                   // float [64]      ref
 constexpr int SM_YCC = SM_CR + 64 * 4;                    // float [48][YS]  y * cc
 constexpr int SM_CC = SM_YCC + 48 * YS * 4;               // float [48][YS]  1/(sigma sqrt2)
 constexpr int SM_BAD = SM_CC + 48 * YS * 4;               // uchar [48] (+pad) 1 if any y < 0
-constexpr int SM_MOM = SM_BAD + 64;                       // double [18][nthreads]
-__host__ __device__ constexpr int smem_bytes(int nthreads) { return SM_MOM + 18 * 8 * nthreads; }
+constexpr int SM_MOM = SM_BAD + 64;                       // double [24][nthreads]
+__host__ __device__ constexpr int smem_bytes(int nthreads) { return SM_MOM + 24 * 8 * nthreads; }
 constexpr int K2P_SLOT = 60;
 
 // ------------------------------------------------------------------------------------
@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(VARIANT == 0 ? 256 : 128, VARIANT == 0 ? 2 : 3
     const double* __restrict__ sMu = p.mu;
     double* sMom = reinterpret_cast<double*>(smem + SM_MOM);
 #pragma unroll
-    for (int m = 0; m < 18; m++) sMom[m * nthr + tid] = 0.0;
+    for (int m = 0; m < 24; m++) sMom[m * nthr + tid] = 0.0;
 
     int roi[SLOTS];
     float q[2][SLOTS], scale[2][SLOTS];
@@ -612,10 +612,11 @@ __global__ void __launch_bounds__(VARIANT == 0 ? 256 : 128, VARIANT == 0 ? 2 : 3
 #pragma unroll
                 for (int s = 0; s < SLOTS; s++) {
                     const double x = (double)q[b][s] - sMu[b * 48 + roi[s]];
-                    const int m = (b * SLOTS + s) * 3;
+                    const int m = (b * SLOTS + s) * 4;
                     sMom[(m + 0) * nthr + tid] += x;
                     sMom[(m + 1) * nthr + tid] += x * x;
                     if (have_prev) sMom[(m + 2) * nthr + tid] += x * ((double)prev[b][s] - sMu[b * 48 + roi[s]]);
+                    else sMom[(m + 3) * nthr + tid] = x;      // first draw of this launch
                     prev[b][s] = q[b][s];
                 }
             have_prev = true;
@@ -648,10 +649,13 @@ __global__ void __launch_bounds__(VARIANT == 0 ? 256 : 128, VARIANT == 0 ? 2 : 3
                     const int nb = p.sweep0 + p.n_sweeps - max(p.sweep0, p.tune_until);   // draws this launch
                     if (nb > 0) {
                         float* mo = p.mom + ((cg * 2 + p.mom_half) * 96 + b * 48 + roi[s]) * 3;
-                        const int m = (b * SLOTS + s) * 3;
+                        const int m = (b * SLOTS + s) * 4;
                         const double sum = sMom[(m + 0) * nthr + tid], sq = sMom[(m + 1) * nthr + tid],
-                                     lag = sMom[(m + 2) * nthr + tid];
-                        const double mean_b = sum / nb, M2_b = sq - sum * mean_b, C1_b = lag - (nb - 1) * mean_b * mean_b;
+                                     lag = sMom[(m + 2) * nthr + tid], x0 = sMom[(m + 3) * nthr + tid];
+                        const double xl = (double)q[b][s] - sMu[b * 48 + roi[s]];
+                        const double mean_b = sum / nb, M2_b = sq - sum * mean_b;
+                        // sum_t (x_t - m)(x_{t-1} - m), t = 1..nb-1, exactly
+                        const double C1_b = lag - mean_b * (2.0 * sum - x0 - xl) + (nb - 1) * mean_b * mean_b;
                         const double na = p.mom_n_before, n = na + nb;
                         const double mean_a = mo[0], delta = mean_b - mean_a;
                         mo[0] = (float)(mean_a + delta * nb / n);

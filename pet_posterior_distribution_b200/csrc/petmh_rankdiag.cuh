@@ -1,0 +1,317 @@
+// petmh_rankdiag.cuh -- K3, stored-draw diagnostics on the GPU: rank-normalised split R-hat,
+// bulk / tail / mean effective sample sizes and MCSE as ArviZ computes them for
+// pm.summary / pm.rhat (mcmc.py:181,186-187; Vehtari et al. 2021).  PARITY UNPINNED
+// (arviz is third-party and absent): checked against oracle/diagnostics.py only.
+//
+// Per (TAC, coordinate) segment: the C chains x N stored draws are split in halves
+// (2C chains of h = N/2; an odd middle draw is dropped), globally ranked with ties averaged
+// (one 64-bit-key radix sort over all segments: key = segment << 32 | order-preserving
+// float bits), mapped through the inverse normal cdf, and fed to the Geyer-truncated
+// autocorrelation sum.  Not a hot path: clarity over speed.
+#pragma once
+#include <algorithm>
+#include <cub/cub.cuh>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+namespace petmh {
+
+struct RankDiagParams {
+    const float* draws;   // [S*C][max_draws][96]
+    int n_chains, max_draws, n_stored;
+    int tac0, n_tac;      // TAC batch
+    int h;                // half length
+    int L;                // 2*C*h values per segment
+};
+
+__device__ __forceinline__ uint32_t f2sortable(float f) {
+    uint32_t u = __float_as_uint(f);
+    return u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float sortable2f(uint32_t u) {
+    u ^= ((u >> 31) ? 0x80000000u : 0xffffffffu);
+    return __uint_as_float(u);
+}
+
+// element k of a segment -> (chain, draw): split chains ordered [first halves..., second halves...]
+__device__ __forceinline__ float seg_value(const RankDiagParams& p, int seg, int k) {
+    const int tac = p.tac0 + seg / 96, coord = seg % 96;
+    const int sc = k / p.h, i = k - sc * p.h;
+    const int c = sc % p.n_chains;
+    const int d = sc < p.n_chains ? i : p.n_stored - p.h + i;
+    return p.draws[(((size_t)tac * p.n_chains + c) * p.max_draws + d) * 96 + coord];
+}
+
+// mode 0: x; mode 1: |x - median|
+__global__ void rd_build_keys(const RankDiagParams p, int mode, const float* med, float* xs, unsigned long long* keys,
+                              uint32_t* vals, size_t n) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int seg = (int)(e / p.L), k = (int)(e - (size_t)seg * p.L);
+    float x = seg_value(p, seg, k);
+    if (mode == 0) xs[e] = x;
+    else x = fabsf(x - med[seg]);
+    keys[e] = ((unsigned long long)seg << 32) | f2sortable(x);
+    vals[e] = (uint32_t)k;
+}
+
+// sorted keys/vals -> z-scores scattered back to original positions (ties: average rank)
+__global__ void rd_ranks(const unsigned long long* keys, const uint32_t* vals, float* z, int L, size_t n) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const size_t seg0 = (e / L) * (size_t)L;
+    if (e != seg0 && keys[e - 1] == keys[e]) return;   // not a run start
+    size_t b = e + 1;
+    const size_t seg_end = seg0 + L;
+    while (b < seg_end && keys[b] == keys[e]) b++;
+    const double rank = 0.5 * ((double)(e - seg0) + (double)(b - 1 - seg0)) + 1.0;
+    const float zz = (float)normcdfinv((rank - 0.375) / ((double)L + 0.25));
+    for (size_t q = e; q < b; q++) z[seg0 + vals[q]] = zz;
+}
+
+// per segment: median, q05, q95 (numpy linear-interpolation quantiles) from the sorted keys
+__global__ void rd_quantiles(const unsigned long long* keys, int L, int nseg, float* med, float* q05, float* q95) {
+    const int seg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (seg >= nseg) return;
+    const unsigned long long* k = keys + (size_t)seg * L;
+    auto at = [&](int i) { return (double)sortable2f((uint32_t)k[i]); };
+    auto quant = [&](double q) {
+        const double pos = q * (L - 1);
+        const int lo = (int)floor(pos);
+        const int hi = min(lo + 1, L - 1);
+        const double fr = pos - lo;
+        return (float)(at(lo) + (at(hi) - at(lo)) * fr);
+    };
+    med[seg] = quant(0.5);
+    q05[seg] = quant(0.05);
+    q95[seg] = quant(0.95);
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+    const int tid = threadIdx.x;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((tid & 31) == 0) sh[tid >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += sh[w];
+    return t;
+}
+
+// series value of type ty at element e: 0 = z (bulk), 1 = x <= q05, 2 = x <= q95, 3 = x
+__device__ __forceinline__ float series(int ty, const float* xs, const float* z, float q05, float q95, size_t e) {
+    if (ty == 0) return z[e];
+    if (ty == 3) return xs[e];
+    const float x = xs[e];
+    return (ty == 1 ? x <= q05 : x <= q95) ? 1.f : 0.f;
+}
+
+// rank-normalised split R-hat: max of bulk (z) and tail (z of folded); one CTA per segment
+__global__ void rd_rhat(const float* z, const float* zf, int m, int h, float* rhat_out) {
+    __shared__ double sh[32];
+    const int seg = blockIdx.x;
+    float best = 0.f;
+    for (int which = 0; which < 2; which++) {
+        const float* a = (which ? zf : z) + (size_t)seg * m * h;
+        double sum_mean = 0, sum_mean2 = 0, sum_var = 0;
+        for (int c = 0; c < m; c++) {
+            double s = 0;
+            for (int i = threadIdx.x; i < h; i += blockDim.x) s += a[(size_t)c * h + i];
+            const double mean = block_sum(s, sh) / h;
+            double q = 0;
+            for (int i = threadIdx.x; i < h; i += blockDim.x) { const double d = a[(size_t)c * h + i] - mean; q += d * d; }
+            const double var = block_sum(q, sh) / (h - 1);
+            sum_mean += mean; sum_mean2 += mean * mean; sum_var += var;
+        }
+        const double between = (double)h * (sum_mean2 - sum_mean * sum_mean / m) / (m - 1);
+        const double within = sum_var / m;
+        const float r = (float)sqrt((between / within + h - 1) / h);
+        best = which == 0 ? r : fmaxf(best, r);
+    }
+    if (threadIdx.x == 0) rhat_out[seg] = best;
+}
+
+// arviz _ess for one (segment, series type); blockDim.x = ESS_LB lags per batch
+constexpr int ESS_LB = 256;
+__global__ void __launch_bounds__(ESS_LB) rd_ess(const float* xs, const float* z, const float* q05, const float* q95, int m,
+                                                 int h, float* rho_scratch /*[nseg*4][h]*/, float* ess_out /*[nseg][4]*/) {
+    __shared__ double sh[32];
+    __shared__ double cmean[512];
+    __shared__ int s_stop, s_t;
+    __shared__ double s_even, s_odd;
+    const int seg = blockIdx.x >> 2, ty = blockIdx.x & 3, tid = threadIdx.x;
+    const size_t base = (size_t)seg * m * h;
+    const float a05 = q05[seg], a95 = q95[seg];
+    float* rho = rho_scratch + (size_t)blockIdx.x * h;
+    // chain means, biased variances
+    double sum_mean = 0, sum_mean2 = 0, acov0 = 0;
+    for (int c = 0; c < m; c++) {
+        double s = 0;
+        for (int i = tid; i < h; i += blockDim.x) s += series(ty, xs, z, a05, a95, base + (size_t)c * h + i);
+        const double mean = block_sum(s, sh) / h;
+        double q = 0;
+        for (int i = tid; i < h; i += blockDim.x) { const double d = series(ty, xs, z, a05, a95, base + (size_t)c * h + i) - mean; q += d * d; }
+        const double v = block_sum(q, sh) / h;
+        if (tid == 0 && c < 512) cmean[c] = mean;
+        sum_mean += mean; sum_mean2 += mean * mean; acov0 += v;
+    }
+    __syncthreads();
+    const double mean_var = acov0 / m * h / (h - 1.0);
+    double var_plus = mean_var * (h - 1.0) / h;
+    if (m > 1) var_plus += (sum_mean2 - sum_mean * sum_mean / m) / (m - 1);
+    const double ntot = (double)m * h;
+    if (!(var_plus > 0.0) || h < 4) {
+        if (tid == 0) ess_out[seg * 4 + ty] = CUDART_NAN_F;
+        return;
+    }
+    if (tid == 0) { s_stop = 0; s_t = 1; s_even = 1.0; s_odd = 0.0; rho[0] = 1.f; }
+    __syncthreads();
+    int have = 0;   // lags [1, have] available in rho as raw "1 - (mean_var - acov)/var_plus"
+    int max_t = -1;
+    while (true) {
+        // compute lags have+1 .. have+ESS_LB
+        const int t = have + 1 + tid;
+        double acc = 0.0;
+        if (t < h) {
+            for (int c = 0; c < m; c++) {
+                const double mu = cmean[min(c, 511)];
+                const size_t o = base + (size_t)c * h;
+                double a = 0.0;
+                for (int n = 0; n + t < h; n++)
+                    a += (series(ty, xs, z, a05, a95, o + n) - mu) * (series(ty, xs, z, a05, a95, o + n + t) - mu);
+                acc += a / h;
+            }
+            rho[t] = (float)(1.0 - (mean_var - acc / m) / var_plus);
+        }
+        __syncthreads();
+        have = min(have + ESS_LB, h - 1);
+        if (tid == 0) {
+            // Geyer's initial positive sequence, resumed where it stopped
+            int tt = s_t;
+            double even = s_even, odd = s_odd;
+            if (tt == 1 && s_odd == 0.0) { odd = rho[1]; }
+            bool stop = false;
+            while (true) {
+                if (!(tt < (h - 3) && (even + odd) > 0.0)) { stop = true; break; }
+                if (tt + 2 > have) break;                       // need more lags
+                even = rho[tt + 1];
+                odd = rho[tt + 2];
+                if (!((even + odd) >= 0.0)) { rho[tt + 1] = 0.f; rho[tt + 2] = 0.f; }
+                tt += 2;
+            }
+            s_t = tt; s_even = even; s_odd = odd; s_stop = stop ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_stop || have >= h - 1) break;
+    }
+    if (tid == 0) {
+        const int tt = s_t;
+        max_t = tt - 2;
+        // raw values beyond the accepted prefix must read as zero (arviz's rho_hat_t is zero-initialised)
+        const double even = s_even;
+        if (even > 0 && max_t + 1 >= 0 && max_t + 1 < h) rho[max_t + 1] = (float)even;
+        // initial monotone sequence
+        int t2 = 1;
+        while (t2 <= max_t - 2) {
+            if ((rho[t2 + 1] + rho[t2 + 2]) > (rho[t2 - 1] + rho[t2])) {
+                rho[t2 + 1] = (rho[t2 - 1] + rho[t2]) / 2.f;
+                rho[t2 + 2] = rho[t2 + 1];
+            }
+            t2 += 2;
+        }
+        double ssum = 0.0;
+        for (int i = 0; i <= max_t; i++) ssum += rho[i];
+        double tau = -1.0 + 2.0 * ssum + ((max_t + 1 >= 0 && max_t + 1 < h) ? (double)rho[max_t + 1] : 0.0);
+        tau = fmax(tau, 1.0 / log10(ntot));
+        ess_out[seg * 4 + ty] = (float)(ntot / tau);
+    }
+}
+
+// pooled mean / sd (ddof = 1) of a segment's values + assembly of the 8-column row
+__global__ void rd_finalize(const float* xs, int L, const float* ess, const float* rhat, const uint32_t* nacc,
+                            const float* scale, int n_chains, int tac0, int n_draw_sweeps, float* out) {
+    __shared__ double sh[32];
+    const int seg = blockIdx.x;
+    const float* a = xs + (size_t)seg * L;
+    double s = 0;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) s += a[i];
+    const double mean = block_sum(s, sh) / L;
+    double q = 0;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) { const double d = a[i] - mean; q += d * d; }
+    const double sd = sqrt(block_sum(q, sh) / (L - 1));
+    if (threadIdx.x == 0) {
+        const int tac = tac0 + seg / 96, coord = seg % 96;
+        double acc = 0, sc = 0;
+        for (int c = 0; c < n_chains; c++) {
+            acc += nacc[((size_t)tac * n_chains + c) * 96 + coord];
+            sc += scale[((size_t)tac * n_chains + c) * 96 + coord];
+        }
+        float* o = out + ((size_t)tac * 96 + coord) * 8;
+        o[0] = (float)mean;
+        o[1] = (float)sd;
+        o[2] = (float)(sd / sqrt((double)ess[seg * 4 + 3]));
+        o[3] = ess[seg * 4 + 0];
+        o[4] = fminf(ess[seg * 4 + 1], ess[seg * 4 + 2]);
+        o[5] = rhat[seg];
+        o[6] = n_draw_sweeps > 0 ? (float)(acc / ((double)n_chains * n_draw_sweeps)) : CUDART_NAN_F;
+        o[7] = (float)(sc / n_chains);
+    }
+}
+
+// Host driver.  Returns a cudaError_t (0 = ok).
+static inline int launch_rank_summary(const float* d_draws, int n_tac_total, int n_chains, int max_draws, int n_stored,
+                                      const uint32_t* nacc, const float* scale, int n_draw_sweeps, float* d_out,
+                                      cudaStream_t st) {
+    const int h = n_stored / 2;
+    const int m = 2 * n_chains;
+    const int L = m * h;
+    if (h < 4 || m > 512) return (int)cudaErrorInvalidValue;
+    const size_t max_elems = (size_t)1 << 27;
+    int tacs_per_batch = (int)std::max<size_t>(1, max_elems / ((size_t)96 * L));
+    tacs_per_batch = std::min(tacs_per_batch, n_tac_total);
+    const size_t nseg_b = (size_t)tacs_per_batch * 96, nmax = nseg_b * L;
+    float *xs = nullptr, *z = nullptr, *zf = nullptr, *med = nullptr, *q05 = nullptr, *q95 = nullptr, *rho = nullptr, *ess = nullptr,
+          *rhat = nullptr;
+    unsigned long long *k0 = nullptr, *k1 = nullptr;
+    uint32_t *v0 = nullptr, *v1 = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    cudaError_t e = cudaSuccess;
+#define RD(call) do { e = (call); if (e != cudaSuccess) goto done; } while (0)
+    RD(cudaMalloc(&xs, nmax * 4)); RD(cudaMalloc(&z, nmax * 4)); RD(cudaMalloc(&zf, nmax * 4));
+    RD(cudaMalloc(&k0, nmax * 8)); RD(cudaMalloc(&k1, nmax * 8)); RD(cudaMalloc(&v0, nmax * 4)); RD(cudaMalloc(&v1, nmax * 4));
+    RD(cudaMalloc(&med, nseg_b * 4)); RD(cudaMalloc(&q05, nseg_b * 4)); RD(cudaMalloc(&q95, nseg_b * 4));
+    RD(cudaMalloc(&rho, nseg_b * 4 * (size_t)h * 4)); RD(cudaMalloc(&ess, nseg_b * 4 * 4)); RD(cudaMalloc(&rhat, nseg_b * 4));
+    {
+        int seg_bits = 1;
+        while (((size_t)1 << seg_bits) < nseg_b) seg_bits++;
+        RD(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k0, k1, v0, v1, nmax, 0, 32 + seg_bits, st));
+        RD(cudaMalloc(&tmp, tmp_bytes));
+        for (int t0 = 0; t0 < n_tac_total; t0 += tacs_per_batch) {
+            RankDiagParams p{d_draws, n_chains, max_draws, n_stored, t0, std::min(tacs_per_batch, n_tac_total - t0), h, L};
+            const int nseg = p.n_tac * 96;
+            const size_t n = (size_t)nseg * L;
+            const unsigned gb = (unsigned)((n + 255) / 256);
+            rd_build_keys<<<gb, 256, 0, st>>>(p, 0, nullptr, xs, k0, v0, n);
+            RD(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k0, k1, v0, v1, n, 0, 32 + seg_bits, st));
+            rd_ranks<<<gb, 256, 0, st>>>(k1, v1, z, L, n);
+            rd_quantiles<<<(nseg + 127) / 128, 128, 0, st>>>(k1, L, nseg, med, q05, q95);
+            rd_build_keys<<<gb, 256, 0, st>>>(p, 1, med, xs, k0, v0, n);
+            RD(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k0, k1, v0, v1, n, 0, 32 + seg_bits, st));
+            rd_ranks<<<gb, 256, 0, st>>>(k1, v1, zf, L, n);
+            rd_rhat<<<nseg, 256, 0, st>>>(z, zf, m, h, rhat);
+            rd_ess<<<nseg * 4, ESS_LB, 0, st>>>(xs, z, q05, q95, m, h, rho, ess);
+            rd_finalize<<<nseg, 256, 0, st>>>(xs, L, ess, rhat, nacc, scale, n_chains, t0, n_draw_sweeps, d_out);
+            RD(cudaGetLastError());
+        }
+        RD(cudaStreamSynchronize(st));
+    }
+done:
+#undef RD
+    cudaFree(xs); cudaFree(z); cudaFree(zf); cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1); cudaFree(med);
+    cudaFree(q05); cudaFree(q95); cudaFree(rho); cudaFree(ess); cudaFree(rhat); cudaFree(tmp);
+    return (int)e;
+}
+
+}  // namespace petmh
