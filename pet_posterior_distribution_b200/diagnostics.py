@@ -1,0 +1,82 @@
+"""Host-side writers for the reference's side outputs (mcmc.py:162-194): the per-sample
+pickle, the ArviZ-style ``_summary.csv`` and the ``rhat_less_than_102.txt`` log.
+
+mean / sd / mcse_mean / ess_bulk / ess_tail / r_hat come from the GPU (K3, petmh_get_summary);
+the two remaining pm.summary columns that need order statistics of the pooled draws
+(hdi_3%, hdi_97%) and mcse_sd are computed here from the chains with numpy.
+"""
+import io
+import os
+
+import numpy as np
+
+
+def hdi(x, prob=0.94):
+    """Narrowest interval containing `prob` of the pooled draws (arviz.hdi, unimodal)."""
+    x = np.sort(np.asarray(x, np.float64).ravel())
+    n = x.size
+    k = int(np.floor(prob * n))
+    if k < 1 or k >= n:
+        return x[0], x[-1]
+    w = x[k:] - x[:n - k]
+    i = int(np.argmin(w))
+    return x[i], x[i + k]
+
+
+def mcse_sd(x, ess_sd):
+    """arviz _mcse_sd: sd * sqrt(e * (1 - 1/ess)^(ess - 1) - 1) with ess = ess_sd."""
+    sd = np.asarray(x, np.float64).std(ddof=1)
+    ess_sd = max(float(ess_sd), 1.0 + 1e-9)
+    fac = np.sqrt(np.exp(1) * (1 - 1 / ess_sd) ** (ess_sd - 1) - 1)
+    return sd * fac
+
+
+def summary_csv(dvr, r1, k2p, gpu_summary, ess_sd=None):
+    """CSV text with pm.summary's layout: rows var_DVR[i], var_R1[i], var_k2p; columns
+    mean, sd, hdi_3%, hdi_97%, mcse_mean, mcse_sd, ess_bulk, ess_tail, r_hat (default rounding:
+    3 decimals, ESS to 0 decimals, r_hat to 2).  dvr/r1: (chains, draws, 48); gpu_summary (96, 8)."""
+    out = io.StringIO()
+    out.write(",mean,sd,hdi_3%,hdi_97%,mcse_mean,mcse_sd,ess_bulk,ess_tail,r_hat\n")
+    for b, (name, arr) in enumerate((("var_DVR", dvr), ("var_R1", r1))):
+        for i in range(arr.shape[-1]):
+            g = gpu_summary[b * 48 + i]
+            lo, hi = hdi(arr[..., i])
+            # ess_sd ~ ess_bulk is the standard fallback when the squared-deviation ESS is not computed
+            msd = mcse_sd(arr[..., i], g[3] if ess_sd is None else ess_sd[b * 48 + i])
+            out.write("%s[%d],%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.1f,%.1f,%.2f\n" %
+                      (name, i, g[0], g[1], lo, hi, g[2], msd, np.round(g[3]), np.round(g[4]), g[5]))
+    k = float(np.asarray(k2p).reshape(-1)[0])
+    out.write("var_k2p,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%s,%s,\n" % (k, 0.0, k, k, 0.0, 0.0, "", ""))
+    return out.getvalue()
+
+
+def append_rhat_log(mcmc_dir, save_name, sample, gpu_summary, threshold=1.02):
+    """mcmc.py:183-194: append a line when any DVR/R1 r_hat exceeds 1.02."""
+    rmax = float(np.nanmax(gpu_summary[:, 5]))
+    if rmax > threshold:
+        with open(os.path.join(mcmc_dir, "rhat_less_than_102.txt"), "at") as f:
+            f.write(save_name + " - sample {} - rhat_max = {:.4f}\n".format(sample, rmax))
+    return rmax
+
+
+class PosteriorStandIn(dict):
+    """Stand-in for arviz.InferenceData when ArviZ is absent: idata.posterior['var_DVR'] etc.
+    work the way mcmc.py:162-164 and main_script.py use them."""
+
+    @property
+    def posterior(self):
+        return self["posterior"]
+
+    @property
+    def sample_stats(self):
+        return self.get("sample_stats", {})
+
+
+def make_idata(dvr, r1, k2p, sample_stats=None):
+    post = {"var_DVR": np.asarray(dvr, np.float64), "var_R1": np.asarray(r1, np.float64),
+            "var_k2p": np.full(dvr.shape[:2], float(np.asarray(k2p).reshape(-1)[0]))}
+    try:                                   # a real InferenceData when ArviZ is importable
+        import arviz as az                 # noqa: F401
+        return az.from_dict(posterior=post, sample_stats=sample_stats or {})
+    except Exception:
+        return PosteriorStandIn(posterior=post, sample_stats=sample_stats or {})

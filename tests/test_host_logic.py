@@ -1,0 +1,118 @@
+"""Host-side logic of the drop-in (no GPU): file naming / discovery / skip rule of mcmc.py,
+summary CSV layout, sharding, and the 2-rank gloo all-gather of summaries."""
+import os
+import pickle
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_mcmc_module_keeps_reference_names():
+    from pet_posterior_distribution_b200 import mcmc
+    for name in ("n_ROI_test", "n_samples_test", "mean_sigma_noise_load", "iter_mcmc", "burn_mcmc", "chains",
+                 "CreateTAC_SRTM2", "NP_DTYPE", "FLAG_PLOT", "CUR_DIR"):
+        assert hasattr(mcmc, name), name
+    assert (mcmc.n_ROI_test, mcmc.n_samples_test, mcmc.iter_mcmc, mcmc.burn_mcmc, mcmc.chains) == (48, 100, 200, 400, 4)
+
+
+def test_save_name_matches_reference_pattern():
+    """mcmc.py:119-123 and the shipped file name MH_MCMC_nROI48_it2.0e+04_brn4.0e+04_km_obs-0.842-0.833-0.013.pik."""
+    from pet_posterior_distribution_b200 import mcmc
+    old = (mcmc.iter_mcmc, mcmc.burn_mcmc)
+    try:
+        mcmc.iter_mcmc, mcmc.burn_mcmc = 20000, 40000
+        name = mcmc.save_name({"DVR": np.array([0.8424]), "R1": np.array([0.8331]), "k2p": np.array([0.0126])})
+        assert name == "MH_MCMC_nROI48_it2.0e+04_brn4.0e+04_km_obs-0.842-0.833-0.013.pik"
+    finally:
+        mcmc.iter_mcmc, mcmc.burn_mcmc = old
+
+
+def test_find_test_file_takes_latest(tmp_path):
+    from pet_posterior_distribution_b200 import mcmc
+    for d in ("25-01-01_00-00-00_test", "25-07-10_15-38-57_test", "25-09-09_00-00-00_train"):
+        p = tmp_path / "sim_data" / "nROI48" / d
+        p.mkdir(parents=True)
+        (p / "data_nROI48_n100_s1.0e-01.pik").write_bytes(b"x")
+    d, f = mcmc.find_test_file(str(tmp_path / "sim_data"))
+    assert d.endswith("25-07-10_15-38-57_test") and f == "data_nROI48_n100_s1.0e-01.pik"
+    with pytest.raises(IndexError):
+        mcmc.find_test_file(str(tmp_path / "nowhere"))
+
+
+def test_summary_csv_layout():
+    from pet_posterior_distribution_b200 import diagnostics
+    rng = np.random.default_rng(0)
+    dvr = 1 + 0.01 * rng.standard_normal((4, 50, 48))
+    r1 = 0.8 + 0.01 * rng.standard_normal((4, 50, 48))
+    g = np.zeros((96, 8), np.float32)
+    g[:, 0] = np.concatenate([dvr.mean((0, 1)), r1.mean((0, 1))]); g[:, 1] = 0.01; g[:, 2] = 1e-3
+    g[:, 3] = 180.4; g[:, 4] = 150.6; g[:, 5] = 1.004
+    txt = diagnostics.summary_csv(dvr, r1, [0.0126], g)
+    lines = txt.strip().split("\n")
+    assert lines[0] == ",mean,sd,hdi_3%,hdi_97%,mcse_mean,mcse_sd,ess_bulk,ess_tail,r_hat"
+    assert len(lines) == 1 + 97 and lines[1].startswith("var_DVR[0],") and lines[49].startswith("var_R1[0],")
+    assert lines[97].startswith("var_k2p,0.013,")
+    f = lines[1].split(",")
+    assert f[7] == "180.0" and f[8] == "151.0" and f[9] == "1.00"
+    lo, hi = diagnostics.hdi(rng.standard_normal(100000))
+    assert abs(lo + 1.88) < 0.05 and abs(hi - 1.88) < 0.05
+
+
+def test_rhat_log(tmp_path):
+    from pet_posterior_distribution_b200 import diagnostics
+    g = np.ones((96, 8), np.float32)
+    g[:, 5] = 1.01
+    assert diagnostics.append_rhat_log(str(tmp_path), "f.pik", 3, g) < 1.02
+    assert not (tmp_path / "rhat_less_than_102.txt").exists()
+    g[5, 5] = 1.0345
+    diagnostics.append_rhat_log(str(tmp_path), "f.pik", 3, g)
+    assert (tmp_path / "rhat_less_than_102.txt").read_text() == "f.pik - sample 3 - rhat_max = 1.0345\n"
+
+
+def test_idata_stand_in():
+    from pet_posterior_distribution_b200 import diagnostics
+    idata = diagnostics.make_idata(np.zeros((4, 10, 48)), np.ones((4, 10, 48)), [0.0126])
+    assert np.asarray(idata.posterior["var_DVR"]).shape == (4, 10, 48)       # mcmc.py:162
+    assert np.asarray(idata.posterior["var_k2p"]).shape == (4, 10)
+    pickle.loads(pickle.dumps(idata))
+
+
+def test_shard_bounds_cover_everything():
+    from pet_posterior_distribution_b200.distributed import shard_bounds, shard_sizes
+    for n in (0, 1, 7, 100, 1048576):
+        for w in (1, 2, 3, 8):
+            b = [shard_bounds(n, w, r) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            assert max(shard_sizes(n, w)) - min(shard_sizes(n, w)) <= 1
+
+
+_GLOO = r"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from pet_posterior_distribution_b200.distributed import shard_bounds, gather_summaries
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+n = 7                                     # 7 TACs over 2 ranks: ragged shards (4 + 3)
+lo, hi = shard_bounds(n, world, rank)
+full = torch.arange(n * 96 * 8, dtype=torch.float32).view(n, 96, 8)
+got = gather_summaries(full[lo:hi].clone(), n)
+assert torch.equal(got, full), "rank %%d: gathered summaries differ" %% rank
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_two_rank_gloo_gather(tmp_path):
+    """N > 1 path on CPU: world_size 2, gloo, ragged TAC shards, all-gather of summaries."""
+    script = tmp_path / "g.py"
+    script.write_text(_GLOO % ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29617", str(script)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2
