@@ -113,6 +113,19 @@ def mcse_mean(a):
     return a.std(ddof=1) / np.sqrt(ess_mean(a))
 
 
+def ess_sd(a):
+    """arviz _ess_sd: min of the mean-ESS of the draws and of their squared deviations."""
+    a = np.asarray(a, np.float64)
+    return min(ess_mean(a), ess_mean((a - a.mean()) ** 2))
+
+
+def mcse_sd(a):
+    """arviz _mcse_sd: sd * sqrt(e (1 - 1/ess)^(ess-1) - 1), ess = ess_sd."""
+    a = np.asarray(a, np.float64)
+    e = ess_sd(a)
+    return a.std(ddof=1) * np.sqrt(np.exp(1) * (1 - 1 / e) ** (e - 1) - 1)
+
+
 def summary_row(a):
     """mean, sd, mcse_mean, ess_bulk, ess_tail, r_hat -- the GPU summary's first six columns."""
     a = np.asarray(a, np.float64)
