@@ -233,7 +233,7 @@ extern "C" int petmh_create(const petmh_cfg* cfg, petmh_t** out) {
     CUC(cudaMalloc(&h->d_scratch64, NT * NT * sizeof(double)));
     CUC(cudaFuncSetAttribute(mh_sweep_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(256)));
     CUC(cudaFuncSetAttribute(mh_sweep_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(128)));
-    CUC(cudaFuncSetAttribute(forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_MOM + 32 * SLOTS * NT * 4));
+    CUC(cudaFuncSetAttribute(forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_STATE + 32 * SLOTS * NT * 4));
 #undef CUC
     *out = h;
     return PETMH_OK;
@@ -427,7 +427,7 @@ static int run_forward(petmh_t* h, int tac, const double* dvr, const double* r1,
     float* d_in = h->d_scratch + 48 * NT + 64;
     CU(cudaMemcpyAsync(d_in, in, sizeof in, cudaMemcpyHostToDevice, h->stream));
     SweepParams p = base_params(h);
-    forward_kernel<<<1, 64, SM_MOM + 32 * SLOTS * NT * 4, h->stream>>>(p, tac, d_in, d_in + 48, h->d_scratch, h->d_scratch + 48 * NT);
+    forward_kernel<<<1, 64, SM_STATE + 32 * SLOTS * NT * 4, h->stream>>>(p, tac, d_in, d_in + 48, h->d_scratch, h->d_scratch + 48 * NT);
     CU(cudaGetLastError());
     tac_out.resize(48 * NT);
     ll_out.resize(48);

@@ -18,6 +18,7 @@
 //  * Philox4x32-10 counter-based randoms keyed by (seed; coord, sweep/block, chain gid).
 #pragma once
 #include <cuda_runtime.h>
+#include <math_constants.h>
 #include <stdint.h>
 #include "m_schedule.inc"
 
@@ -169,8 +170,7 @@ constexpr int SM_CR = SM_M + MPACK * 4;                   // float [64]      ref
 constexpr int SM_YCC = SM_CR + 64 * 4;                    // float [48][YS]  y * cc
 constexpr int SM_CC = SM_YCC + 48 * YS * 4;               // float [48][YS]  1/(sigma sqrt2)
 constexpr int SM_BAD = SM_CC + 48 * YS * 4;               // uchar [48] (+pad) 1 if any y < 0
-constexpr int SM_MOM = SM_BAD + 64;                       // double [24][nthreads]
-__host__ __device__ constexpr int smem_bytes(int nthreads) { return SM_MOM + 24 * 8 * nthreads; }
+constexpr int SM_STATE = SM_BAD + 64;                     // float [ST_WORDS][nthreads] per-thread chain state
 constexpr int K2P_SLOT = 60;
 
 // ------------------------------------------------------------------------------------
@@ -412,9 +412,18 @@ __device__ __forceinline__ float tune_factor(int c) {
 
 // ------------------------------------------------------------------------------------
 // The fused sweep kernel.  blockDim.x = 32*NW; one CTA = 2*NW chains of one TAC.
+//
+// Per-thread chain state lives in shared memory (word w of thread t at st[w*nthr + t], so
+// every access is conflict-free) and only the current block's copy is in registers:
+//   block b (b = 0 DVR, 1 R1), words b*18 + ...: q[3] f32, scale[3] f32, cnt[3] i32,
+//   nacc[3] u32, r[3] f64 (6 words)
+//   words 36..71: per coordinate c = b*3+slot: sum, sumsq, lag, ref, first, prev (f32,
+//   running moments of q - ref over this launch's draw sweeps)
 // ------------------------------------------------------------------------------------
-// VARIANT 0: 256-thread CTAs, 2 CTAs/SM (128-register cap, eval3 spills a little);
-// VARIANT 1: 128-thread CTAs, 3 CTAs/SM (168-register cap, no spills).
+constexpr int ST_BLOCK = 18, ST_MOM = 36, ST_WORDS = 72;
+__host__ __device__ constexpr int smem_bytes(int nthreads) { return SM_STATE + ST_WORDS * 4 * nthreads; }
+
+// VARIANT 0: 256-thread CTAs, 2 CTAs/SM (128-register cap); VARIANT 1: 128-thread CTAs, 3 CTAs/SM (168).
 template <int VARIANT>
 __global__ void __launch_bounds__(VARIANT == 0 ? 256 : 128, VARIANT == 0 ? 2 : 3) mh_sweep_kernel(const SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -434,237 +443,232 @@ __global__ void __launch_bounds__(VARIANT == 0 ? 256 : 128, VARIANT == 0 ? 2 : 3
                                    (unsigned long long)(active ? chain : 0);
 
     load_tac_image(p, tac, smem, tid, nthr);
-    const double* __restrict__ sP = p.P;     // [2][48][48] fp64, L1/L2 resident (37 KB)
-    const double* __restrict__ sMu = p.mu;
-    double* sMom = reinterpret_cast<double*>(smem + SM_MOM);
-#pragma unroll
-    for (int m = 0; m < 24; m++) sMom[m * nthr + tid] = 0.0;
+    float* st = reinterpret_cast<float*>(smem + SM_STATE) + tid;
+#define ST_F(w) st[(w) * nthr]
+#define ST_I(w) reinterpret_cast<int*>(st)[(w) * nthr]
+#define ST_U(w) reinterpret_cast<unsigned*>(st)[(w) * nthr]
 
-    int roi[SLOTS];
-    float q[2][SLOTS], scale[2][SLOTS];
-    int cnt[2][SLOTS];
-    uint32_t nacc[2][SLOTS];
-#pragma unroll
-    for (int s = 0; s < SLOTS; s++) roi[s] = s * 16 + l16;
-#pragma unroll
-    for (int b = 0; b < 2; b++)
-#pragma unroll
-        for (int s = 0; s < SLOTS; s++) {
-            const size_t o = cg * 96 + b * 48 + roi[s];
-            if (TAPED) {   // pymc start: prior mean, scaling 1
-                q[b][s] = (float)sMu[b * 48 + roi[s]];
-                scale[b][s] = 1.0f;
-                cnt[b][s] = 0;
-            } else {
-                q[b][s] = p.q[o];
-                scale[b][s] = p.scale[o];
-                cnt[b][s] = p.cnt[o];
-            }
-            nacc[b][s] = 0;
-        }
-    // r = P (q - mu) in fp64: stage q of the chain through shuffles
-    double r[2][SLOTS];
-#pragma unroll
-    for (int b = 0; b < 2; b++) {
-#pragma unroll
-        for (int s = 0; s < SLOTS; s++) r[b][s] = 0.0;
-#pragma unroll
-        for (int s2 = 0; s2 < SLOTS; s2++) {
-            for (int l2 = 0; l2 < 16; l2++) {
-                const float qv = __shfl_sync(0xffffffffu, q[b][s2], (half << 4) | l2);
-                const int j = s2 * 16 + l2;
-                const double dq = (double)qv - sMu[b * 48 + j];
-#pragma unroll
-                for (int s = 0; s < SLOTS; s++) r[b][s] = fma(sP[(b * 48 + j) * 48 + roi[s]], dq, r[b][s]);
-            }
-        }
-    }
+    // ---- load chain state; r = P (q - mu) in fp64 (q staged through shuffles) ----
     float ll_old[SLOTS];
     {
-        const float3 v = eval3<VARIANT>(l16, q[0][0], q[0][1], q[0][2], q[1][0], q[1][1], q[1][2], nullptr);
-        ll_old[0] = v.x; ll_old[1] = v.y; ll_old[2] = v.z;
-    }
-    float prev[2][SLOTS];   // previous recorded draw (lag-1 products)
-#pragma unroll
-    for (int b = 0; b < 2; b++)
-#pragma unroll
-        for (int s = 0; s < SLOTS; s++) prev[b][s] = q[b][s];
-    bool have_prev = false;
-
-    for (int it = 0; it < p.n_sweeps; it++) {
-        const int sweep = p.sweep0 + it;
-        const bool tuning = sweep < p.tune_until;
-#pragma unroll
-        for (int b = 0; b < 2; b++) {
-            // ---- pymc Metropolis.astep: tune every 100 steps while tuning ----
-            if (tuning && sweep > 0 && (sweep % TUNE_INTERVAL) == 0) {
-#pragma unroll
-                for (int s = 0; s < SLOTS; s++) {
-                    scale[b][s] = __fmul_rn(scale[b][s], tune_factor(cnt[b][s]));
-                    cnt[b][s] = 0;
-                }
-            }
-            // ---- randoms ----
-            float nrm[SLOTS], logu[SLOTS];
-            uint32_t key[SLOTS];
-#pragma unroll
-            for (int s = 0; s < SLOTS; s++) {
-                if (TAPED) {
-                    const size_t o = (((size_t)chain * p.tape_sweeps + sweep) * 2 + b) * 48 + roi[s];
-                    nrm[s] = active ? p.tape_n[o] : 0.f;
-                    logu[s] = active ? p.tape_logu[o] : 0.f;
-                    key[s] = ((active ? (uint32_t)p.tape_rank[o] : (uint32_t)roi[s]) << 6) | (uint32_t)roi[s];
-                } else {
-                    const uint4 x = philox4x32_10(
-                        make_uint4((uint32_t)roi[s], (uint32_t)(2 * sweep + b), (uint32_t)gid, (uint32_t)(gid >> 32)),
-                        make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
-                    nrm[s] = sqrtf(-2.f * __logf(u01(x.x))) * __cosf(6.283185307179586f * u01(x.y));
-                    logu[s] = logf(u01(x.z));
-                    key[s] = (x.w & 0xffffffc0u) | (uint32_t)roi[s];
-                }
-            }
-            // ---- proposals: q' = fl32(q + fl32(n * scale)) ----
-            float qn[SLOTS], ll_new[SLOTS];
-#pragma unroll
-            for (int s = 0; s < SLOTS; s++) qn[s] = __fadd_rn(q[b][s], __fmul_rn(nrm[s], scale[b][s]));
-            // ---- phase A ----
-            {
-                const float3 v = b == 0 ? eval3<VARIANT>(l16, qn[0], qn[1], qn[2], q[1][0], q[1][1], q[1][2], nullptr)
-                                        : eval3<VARIANT>(l16, q[0][0], q[0][1], q[0][2], qn[0], qn[1], qn[2], nullptr);
-                ll_new[0] = v.x; ll_new[1] = v.y; ll_new[2] = v.z;
-            }
-            // ---- phase B: resolve visits in key order ----
-            double d[SLOTS], pre[SLOTS];
-            bool valid[SLOTS];
-#pragma unroll
-            for (int s = 0; s < SLOTS; s++) {
-                d[s] = (double)qn[s] - (double)q[b][s];
-                const float dll = ll_new[s] - ll_old[s];
-                valid[s] = (fabsf(dll) <= 3.0e38f);   // finite (NaN/inf -> false): metrop_select's isfinite
-                // accept iff logu < dll - (d r + d^2 Pii/2)  <=>  pre + d r < 0
-                pre[s] = ((double)logu[s] - (double)dll) + 0.5 * d[s] * d[s] * sP[(b * 48 + roi[s]) * 48 + roi[s]];
-            }
-            uint32_t last = 0;        // keys handled so far are <= last (keys are >= 64 in taped mode? no: rank 0 -> key < 64)
-            bool first_round = true;
-            while (true) {
-                uint32_t cand = 0xffffffffu;
-#pragma unroll
-                for (int s = 0; s < SLOTS; s++) {
-                    const bool open = first_round || key[s] > last;
-                    const bool acc = valid[s] && (fma(d[s], r[b][s], pre[s]) < 0.0);
-                    if (open && acc) cand = min(cand, key[s]);
-                }
-                const uint32_t win = __reduce_min_sync(hmask, cand);
-                if (TAPED) {
-                    if (p.dbg_delta != nullptr && active) {
-#pragma unroll
-                        for (int s = 0; s < SLOTS; s++) {
-                            const bool open = first_round || key[s] > last;
-                            if (open && key[s] <= win) {   // decided in this round
-                                const size_t o = ((size_t)chain * p.tape_sweeps + sweep) * 96 + b * 48 + roi[s];
-                                p.dbg_delta[o] = (float)((double)logu[s] - fma(d[s], r[b][s], pre[s]));
-                                p.dbg_accept[o] = key[s] == win ? 1 : 0;
-                            }
-                        }
-                    }
-                }
-                const bool any_win = win != 0xffffffffu;
-                if (!__any_sync(0xffffffffu, any_win)) break;
-                // broadcast the winner's move and apply it
-                const int wi = (int)(win & 63u);           // winning coordinate (garbage if !any_win)
-                const int wl = wi & 15, ws = wi >> 4;
-                const double dsel = ws == 0 ? d[0] : (ws == 1 ? d[1] : d[2]);
-                const double dw = __shfl_sync(0xffffffffu, dsel, (half << 4) | wl);
-                if (any_win) {
-#pragma unroll
-                    for (int s = 0; s < SLOTS; s++) {
-                        r[b][s] = fma(sP[(b * 48 + wi) * 48 + roi[s]], dw, r[b][s]);
-                        if (key[s] == win) {
-                            q[b][s] = qn[s];
-                            ll_old[s] = ll_new[s];
-                            cnt[b][s] += 1;
-                            if (!tuning) nacc[b][s] += 1;
-                            valid[s] = false;   // spent
-                        }
-                    }
-                    last = win;
-                    first_round = false;
-                } else {
-                    last = 0xfffffffeu;   // this chain is done; keep looping for the other half
-                    first_round = false;
-                }
-            }
-        }
-        // ---- record ----
-        if (TAPED) {
-            if (active) {
-#pragma unroll
-                for (int b = 0; b < 2; b++)
-#pragma unroll
-                    for (int s = 0; s < SLOTS; s++)
-                        p.dbg_draws[((size_t)chain * p.tape_sweeps + sweep) * 96 + b * 48 + roi[s]] = q[b][s];
-            }
-        }
-        if (!tuning) {
-            const int di = sweep - p.tune_until;
-#pragma unroll
-            for (int b = 0; b < 2; b++)
-#pragma unroll
-                for (int s = 0; s < SLOTS; s++) {
-                    const double x = (double)q[b][s] - sMu[b * 48 + roi[s]];
-                    const int m = (b * SLOTS + s) * 4;
-                    sMom[(m + 0) * nthr + tid] += x;
-                    sMom[(m + 1) * nthr + tid] += x * x;
-                    if (have_prev) sMom[(m + 2) * nthr + tid] += x * ((double)prev[b][s] - sMu[b * 48 + roi[s]]);
-                    else sMom[(m + 3) * nthr + tid] = x;      // first draw of this launch
-                    prev[b][s] = q[b][s];
-                }
-            have_prev = true;
-            if (!TAPED && p.draws != nullptr && active && (di % p.thin) == 0) {
-                const int slot = di / p.thin;
-                if (slot < p.max_draws) {
-#pragma unroll
-                    for (int b = 0; b < 2; b++)
-#pragma unroll
-                        for (int s = 0; s < SLOTS; s++)
-                            p.draws[(cg * p.max_draws + slot) * 96 + b * 48 + roi[s]] = q[b][s];
-                }
-            }
-        }
-    }
-    // ---- epilogue: persist state and moments ----
-    if (active) {
+        float q0[2][SLOTS];
 #pragma unroll
         for (int b = 0; b < 2; b++)
 #pragma unroll
             for (int s = 0; s < SLOTS; s++) {
-                const size_t o = cg * 96 + b * 48 + roi[s];
-                if (TAPED) {
-                    p.scale[(size_t)chain * 96 + b * 48 + roi[s]] = scale[b][s];   // scale_out
+                const int i = s * 16 + l16;
+                const size_t o = cg * 96 + b * 48 + i;
+                float qv, sc;
+                int cn;
+                if (TAPED) {   // pymc start: prior mean, scaling 1
+                    qv = (float)p.mu[b * 48 + i]; sc = 1.0f; cn = 0;
                 } else {
-                    p.q[o] = q[b][s];
-                    p.scale[o] = scale[b][s];
-                    p.cnt[o] = (uint8_t)cnt[b][s];
-                    p.nacc[o] += nacc[b][s];
-                    const int nb = p.sweep0 + p.n_sweeps - max(p.sweep0, p.tune_until);   // draws this launch
-                    if (nb > 0) {
-                        float* mo = p.mom + ((cg * 2 + p.mom_half) * 96 + b * 48 + roi[s]) * 3;
-                        const int m = (b * SLOTS + s) * 4;
-                        const double sum = sMom[(m + 0) * nthr + tid], sq = sMom[(m + 1) * nthr + tid],
-                                     lag = sMom[(m + 2) * nthr + tid], x0 = sMom[(m + 3) * nthr + tid];
-                        const double xl = (double)q[b][s] - sMu[b * 48 + roi[s]];
-                        const double mean_b = sum / nb, M2_b = sq - sum * mean_b;
-                        // sum_t (x_t - m)(x_{t-1} - m), t = 1..nb-1, exactly
-                        const double C1_b = lag - mean_b * (2.0 * sum - x0 - xl) + (nb - 1) * mean_b * mean_b;
-                        const double na = p.mom_n_before, n = na + nb;
-                        const double mean_a = mo[0], delta = mean_b - mean_a;
-                        mo[0] = (float)(mean_a + delta * nb / n);
-                        mo[1] = (float)((double)mo[1] + M2_b + delta * delta * na * nb / n);
-                        mo[2] = (float)((double)mo[2] + C1_b);
-                    }
+                    qv = p.q[o]; sc = p.scale[o]; cn = p.cnt[o];
+                }
+                q0[b][s] = qv;
+                ST_F(b * ST_BLOCK + s) = qv;
+                ST_F(b * ST_BLOCK + 3 + s) = sc;
+                ST_I(b * ST_BLOCK + 6 + s) = cn;
+                ST_U(b * ST_BLOCK + 9 + s) = 0u;
+                const int c = b * SLOTS + s;
+                ST_F(ST_MOM + c * 6 + 0) = 0.f; ST_F(ST_MOM + c * 6 + 1) = 0.f; ST_F(ST_MOM + c * 6 + 2) = 0.f;
+                ST_F(ST_MOM + c * 6 + 3) = qv;  ST_F(ST_MOM + c * 6 + 4) = 0.f; ST_F(ST_MOM + c * 6 + 5) = 0.f;
+            }
+#pragma unroll 1
+        for (int b = 0; b < 2; b++) {
+            double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+            const double* Pb = p.P + b * 48 * 48 + l16;
+#pragma unroll 1
+            for (int j = 0; j < 48; j++) {
+                const float mine = (j >> 4) == 0 ? q0[b][0] : ((j >> 4) == 1 ? q0[b][1] : q0[b][2]);
+                const float qv = __shfl_sync(0xffffffffu, mine, (half << 4) | (j & 15));
+                const double dq = (double)qv - p.mu[b * 48 + j];
+                r0 = fma(Pb[j * 48], dq, r0);
+                r1 = fma(Pb[j * 48 + 16], dq, r1);
+                r2 = fma(Pb[j * 48 + 32], dq, r2);
+            }
+            double* rs = reinterpret_cast<double*>(smem + SM_STATE);   // r words are stored as two floats each
+            (void)rs;
+            ST_F(b * ST_BLOCK + 12) = __int_as_float(__double2loint(r0)); ST_F(b * ST_BLOCK + 13) = __int_as_float(__double2hiint(r0));
+            ST_F(b * ST_BLOCK + 14) = __int_as_float(__double2loint(r1)); ST_F(b * ST_BLOCK + 15) = __int_as_float(__double2hiint(r1));
+            ST_F(b * ST_BLOCK + 16) = __int_as_float(__double2loint(r2)); ST_F(b * ST_BLOCK + 17) = __int_as_float(__double2hiint(r2));
+        }
+        const float3 v = eval3<VARIANT>(l16, q0[0][0], q0[0][1], q0[0][2], q0[1][0], q0[1][1], q0[1][2], nullptr);
+        ll_old[0] = v.x; ll_old[1] = v.y; ll_old[2] = v.z;
+    }
+    bool have_prev = false;
+
+#pragma unroll 1
+    for (int it = 0; it < p.n_sweeps; it++) {
+        const int sweep = p.sweep0 + it;
+        const bool tuning = sweep < p.tune_until;
+#pragma unroll 1
+        for (int b = 0; b < 2; b++) {
+            const int sb = b * ST_BLOCK, so = (1 - b) * ST_BLOCK;
+            float q[SLOTS], qn[SLOTS], logu[SLOTS];
+            uint32_t key[SLOTS];
+            // ---- pymc Metropolis.astep: tune every 100 steps while tuning; randoms; proposal ----
+            const bool do_tune = tuning && sweep > 0 && (sweep % TUNE_INTERVAL) == 0;
+#pragma unroll
+            for (int s = 0; s < SLOTS; s++) {
+                const int i = s * 16 + l16;
+                float sc = ST_F(sb + 3 + s);
+                if (do_tune) {
+                    sc = __fmul_rn(sc, tune_factor(ST_I(sb + 6 + s)));
+                    ST_F(sb + 3 + s) = sc;
+                    ST_I(sb + 6 + s) = 0;
+                }
+                float nrm;
+                if (TAPED) {
+                    const size_t o = (((size_t)chain * p.tape_sweeps + sweep) * 2 + b) * 48 + i;
+                    nrm = active ? p.tape_n[o] : 0.f;
+                    logu[s] = active ? p.tape_logu[o] : 0.f;
+                    key[s] = (((active ? (uint32_t)p.tape_rank[o] : (uint32_t)i) + 1u) << 6) | (uint32_t)i;
+                } else {
+                    const uint4 x = philox4x32_10(
+                        make_uint4((uint32_t)i, (uint32_t)(2 * sweep + b), (uint32_t)gid, (uint32_t)(gid >> 32)),
+                        make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+                    nrm = sqrtf(-2.f * __logf(u01(x.x))) * __cosf(6.283185307179586f * u01(x.y));
+                    logu[s] = __logf(u01(x.z));
+                    key[s] = (x.w & 0xffffffc0u) | 0x80000000u | (uint32_t)i;   // > 0, unique, random order
+                }
+                q[s] = ST_F(sb + s);
+                qn[s] = __fadd_rn(q[s], __fmul_rn(nrm, sc));          // q' = fl32(q + fl32(n * scale))
+            }
+            // ---- phase A: log-likelihood at the 3 proposals ----
+            float ll_new[SLOTS];
+            {
+                const float o0 = ST_F(so + 0), o1 = ST_F(so + 1), o2 = ST_F(so + 2);
+                const float3 v = eval3<VARIANT>(l16, b ? o0 : qn[0], b ? o1 : qn[1], b ? o2 : qn[2],
+                                                b ? qn[0] : o0, b ? qn[1] : o1, b ? qn[2] : o2, nullptr);
+                ll_new[0] = v.x; ll_new[1] = v.y; ll_new[2] = v.z;
+            }
+            // ---- phase B: resolve visits in key order ----
+            // accept iff logu < dll - (d r + d^2 Pii / 2)  <=>  pre + d r < 0;  non-finite dll never accepts
+            const double* Pl = p.P + b * 48 * 48 + l16;               // P[b][.][l16 + 16 s]
+            double d[SLOTS], pre[SLOTS], r[SLOTS];
+#pragma unroll
+            for (int s = 0; s < SLOTS; s++) {
+                const int i = s * 16 + l16;
+                d[s] = (double)qn[s] - (double)q[s];
+                const float dll = ll_new[s] - ll_old[s];
+                pre[s] = ((double)logu[s] - (double)dll) + 0.5 * d[s] * d[s] * Pl[i * 48 + 16 * s];
+                r[s] = __hiloint2double(__float_as_int(ST_F(sb + 13 + 2 * s)), __float_as_int(ST_F(sb + 12 + 2 * s)));
+                if (!(fabsf(dll) <= 3.0e38f)) {                       // metrop_select's isfinite guard
+                    if (TAPED && p.dbg_delta != nullptr && active)
+                        p.dbg_delta[((size_t)chain * p.tape_sweeps + sweep) * 96 + b * 48 + i] = CUDART_NAN_F;
+                    key[s] = 0u;                                      // never opens
                 }
             }
+            uint32_t last = 0u;                                       // keys <= last are decided
+            int acc_mask = 0;
+#pragma unroll 1
+            while (true) {
+                uint32_t cand = 0xffffffffu;
+#pragma unroll
+                for (int s = 0; s < SLOTS; s++)
+                    if (key[s] > last && fma(d[s], r[s], pre[s]) < 0.0) cand = min(cand, key[s]);
+                const uint32_t win = __reduce_min_sync(hmask, cand);
+                if (TAPED && p.dbg_delta != nullptr && active) {
+#pragma unroll
+                    for (int s = 0; s < SLOTS; s++)
+                        if (key[s] > last && key[s] <= win) {         // decided in this round
+                            const size_t o = ((size_t)chain * p.tape_sweeps + sweep) * 96 + b * 48 + s * 16 + l16;
+                            p.dbg_delta[o] = (float)((double)logu[s] - fma(d[s], r[s], pre[s]));
+                            p.dbg_accept[o] = key[s] == win ? 1 : 0;
+                        }
+                }
+                const bool any_win = win != 0xffffffffu;
+                if (!__any_sync(0xffffffffu, any_win)) break;
+                const int wi = (int)(win & 63u);                      // winning coordinate (63 if none)
+                const int ws = wi >> 4;
+                const double dsel = ws == 0 ? d[0] : (ws == 1 ? d[1] : d[2]);
+                const double dw = __shfl_sync(0xffffffffu, dsel, (half << 4) | (wi & 15));
+                if (any_win) {
+                    const double* Pc = Pl + wi * 48;
+                    r[0] = fma(Pc[0], dw, r[0]);
+                    r[1] = fma(Pc[16], dw, r[1]);
+                    r[2] = fma(Pc[32], dw, r[2]);
+#pragma unroll
+                    for (int s = 0; s < SLOTS; s++)
+                        if (key[s] == win) acc_mask |= 1 << s;
+                }
+                last = any_win ? win : 0xfffffffeu;                   // a finished chain idles
+            }
+            // ---- commit the block ----
+#pragma unroll
+            for (int s = 0; s < SLOTS; s++) {
+                if (acc_mask & (1 << s)) {
+                    ST_F(sb + s) = qn[s];
+                    ll_old[s] = ll_new[s];
+                    ST_I(sb + 6 + s) = ST_I(sb + 6 + s) + 1;
+                    if (!tuning) ST_U(sb + 9 + s) = ST_U(sb + 9 + s) + 1u;
+                }
+                ST_F(sb + 12 + 2 * s) = __int_as_float(__double2loint(r[s]));
+                ST_F(sb + 13 + 2 * s) = __int_as_float(__double2hiint(r[s]));
+            }
+        }
+        // ---- record ----
+        if (TAPED && active) {
+#pragma unroll
+            for (int c = 0; c < 2 * SLOTS; c++)
+                p.dbg_draws[((size_t)chain * p.tape_sweeps + sweep) * 96 + (c / SLOTS) * 48 + (c % SLOTS) * 16 + l16] =
+                    ST_F((c / SLOTS) * ST_BLOCK + (c % SLOTS));
+        }
+        if (!tuning) {
+            const int di = sweep - p.tune_until;
+            const bool store = !TAPED && p.draws != nullptr && active && (di % p.thin) == 0 && (di / p.thin) < p.max_draws;
+#pragma unroll
+            for (int c = 0; c < 2 * SLOTS; c++) {
+                const float qv = ST_F((c / SLOTS) * ST_BLOCK + (c % SLOTS));
+                const float x = qv - ST_F(ST_MOM + c * 6 + 3);
+                ST_F(ST_MOM + c * 6 + 0) += x;
+                ST_F(ST_MOM + c * 6 + 1) = fmaf(x, x, ST_F(ST_MOM + c * 6 + 1));
+                if (have_prev) ST_F(ST_MOM + c * 6 + 2) = fmaf(x, ST_F(ST_MOM + c * 6 + 5), ST_F(ST_MOM + c * 6 + 2));
+                else ST_F(ST_MOM + c * 6 + 4) = x;                    // first draw of this launch
+                ST_F(ST_MOM + c * 6 + 5) = x;
+                if (store)
+                    p.draws[(cg * p.max_draws + di / p.thin) * 96 + (c / SLOTS) * 48 + (c % SLOTS) * 16 + l16] = qv;
+            }
+            have_prev = true;
+        }
     }
+    // ---- epilogue: persist state and moments ----
+    if (active) {
+        const int nb = p.sweep0 + p.n_sweeps - max(p.sweep0, p.tune_until);   // draws this launch
+#pragma unroll
+        for (int c = 0; c < 2 * SLOTS; c++) {
+            const int b = c / SLOTS, s = c % SLOTS, i = s * 16 + l16;
+            const size_t o = cg * 96 + b * 48 + i;
+            if (TAPED) {
+                p.scale[(size_t)chain * 96 + b * 48 + i] = ST_F(b * ST_BLOCK + 3 + s);   // scale_out
+                continue;
+            }
+            p.q[o] = ST_F(b * ST_BLOCK + s);
+            p.scale[o] = ST_F(b * ST_BLOCK + 3 + s);
+            p.cnt[o] = (uint8_t)ST_I(b * ST_BLOCK + 6 + s);
+            p.nacc[o] += ST_U(b * ST_BLOCK + 9 + s);
+            if (nb > 0) {
+                float* mo = p.mom + ((cg * 2 + p.mom_half) * 96 + b * 48 + i) * 3;
+                const double sum = ST_F(ST_MOM + c * 6 + 0), sq = ST_F(ST_MOM + c * 6 + 1), lag = ST_F(ST_MOM + c * 6 + 2);
+                const double ref = (double)ST_F(ST_MOM + c * 6 + 3) - p.mu[b * 48 + i];   // launch reference about mu
+                const double x0 = ST_F(ST_MOM + c * 6 + 4), xl = ST_F(ST_MOM + c * 6 + 5);
+                const double mean_r = sum / nb;                                        // about ref
+                const double M2_b = sq - sum * mean_r;
+                // sum_t (x_t - m)(x_{t-1} - m), t = 1..nb-1, exactly
+                const double C1_b = lag - mean_r * (2.0 * sum - x0 - xl) + (nb - 1) * mean_r * mean_r;
+                const double mean_b = ref + mean_r;                                    // about mu
+                const double na = p.mom_n_before, n = na + nb;
+                const double mean_a = mo[0], delta = mean_b - mean_a;
+                mo[0] = (float)(mean_a + delta * nb / n);
+                mo[1] = (float)((double)mo[1] + M2_b + delta * delta * na * nb / n);
+                mo[2] = (float)((double)mo[2] + C1_b);
+            }
+        }
+    }
+#undef ST_F
+#undef ST_I
+#undef ST_U
 }
 
 // ------------------------------------------------------------------------------------
@@ -686,7 +690,7 @@ __global__ void forward_kernel(const SweepParams p, int tac, const float* dvr, c
             a[s] = dvr[roi[s]];
             b[s] = r1[roi[s]];
         }
-        float* scratch = reinterpret_cast<float*>(smem + SM_MOM) + tid * SLOTS * NT;
+        float* scratch = reinterpret_cast<float*>(smem + SM_STATE) + tid * SLOTS * NT;
         const float3 v = eval3<0>(l16, a[0], a[1], a[2], b[0], b[1], b[2], scratch);
         ll[0] = v.x; ll[1] = v.y; ll[2] = v.z;
         if (tid < 16) {

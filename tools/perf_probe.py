@@ -19,8 +19,8 @@ k2p = ds["vark2p"].astype(np.float32)[idx]
 s = MHSampler(n_chains=C, max_tacs=S, max_draws=0, seed=1)
 s.set_frames(ds["time_vector"], ds["dt"]); s.set_prior(pr["mu_DVR"], pr["Cov_DVR"], pr["mu_R1"], pr["Cov_R1"])
 s.set_data(y, cr, k2p, ds["sigma_noise"].astype(np.float32))
-s.reset(); s.plan(10**6, 10**6, 1)
-s.advance(WARM)  # warm-up (scale 1: mostly rejections at first)
+s.reset(); s.plan(10**6, WARM, 1)
+s.advance(WARM)  # tuning sweeps (pymc table every 100), then steady-state draw sweeps are timed
 for rep in range(3):
     s.advance(SW)
     ms, nl = s.last_kernel_ms()
