@@ -32,7 +32,7 @@ constexpr int NGRID = 2 * NT;        // 108 resample points (kinetic_model.py:14
 constexpr int MPACK = PETMH_MPACK;
 constexpr int SLOTS = 3;             // ROIs per lane
 constexpr int TUNE_INTERVAL = 100;   // pymc Metropolis tune_interval
-constexpr float Z_CUT = 3.85f;       // erfc(z)/2 < 2^-25 beyond: (1 - h) rounds to 1 in fp32
+constexpr float Z_CUT = 3.5f;        // erfc(z)/2 < 3.7e-7 beyond: below the fp32 rounding of a per-ROI sum (~1e2, ulp 8e-6)
 constexpr int RB = PETMH_RB;          // 18 rows per row block
 constexpr int NBLK = PETMH_NBLK;      // 3 row blocks
 constexpr int RSTRIDE = PETMH_RSTRIDE;// 20 floats per packed column of a block
@@ -107,6 +107,16 @@ __device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) {
 __device__ __forceinline__ void ffma2(u64& d, u64 a, u64 b) {
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
 }
+__device__ __forceinline__ u64 fmul2(u64 a, u64 b) {
+    u64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 ffma2r(u64 a, u64 b, u64 c) {
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -167,7 +177,7 @@ __device__ __forceinline__ float half_erfc(float z) {
 constexpr int SM_CRS = 0;                                 // double [NGRID]
 constexpr int SM_M = SM_CRS + NGRID * 8;                  // float [MPACK]   packed operator
 constexpr int SM_CR = SM_M + MPACK * 4;                   // float [64]      reference TAC, [60] = k2p
-constexpr int SM_YCC = SM_CR + 64 * 4;                    // float [48][YS]  y * cc
+constexpr int SM_YCC = SM_CR + 64 * 4;                    // float [48][YS]  -(y * cc)
 constexpr int SM_CC = SM_YCC + 48 * YS * 4;               // float [48][YS]  1/(sigma sqrt2)
 constexpr int SM_BAD = SM_CC + 48 * YS * 4;               // uchar [48] (+pad) 1 if any y < 0
 constexpr int SM_STATE = SM_BAD + 64;                     // float [ST_WORDS][nthreads] per-thread chain state
@@ -183,36 +193,49 @@ constexpr int K2P_SLOT = 60;
 // ------------------------------------------------------------------------------------
 constexpr int K = SLOTS;
 
-// one frame of one item: TAC assembly, clamp, Gaussian term, z for the truncation term
-#define PETMH_FRAME(conv_, cr_, cc_, yc_, s_, z_)                                            \
-    {                                                                                        \
-        float sv_ = fmaf(coef0, (conv_), r10 * (cr_));   /* kinetic_model.py:157-158 */      \
-        sv_ = sv_ < 0.f ? 1e-6f : sv_;                   /* mcmc.py:152 */                   \
-        const float rs_ = rsqrt_approx(sv_);                                                 \
-        const float uu_ = fmaf(-sv_, (cc_), (yc_)) * rs_; /* (y - s) / (sig sqrt(2 s)) */    \
-        G0 = fmaf(uu_, uu_, G0);                         /* (y-s)^2 / (2 s sig^2) */         \
-        (s_) = sv_;                                                                          \
-        (z_) = sv_ * rs_ * (cc_);                        /* sqrt(s) / (sig sqrt2) */         \
-    }
+// Two consecutive frames of one item in packed fp32x2 arithmetic (FMUL2 / FFMA2):
+// TAC assembly (kinetic_model.py:157-158), clamp (mcmc.py:152), Gaussian term, z = sqrt(s)/(sig sqrt2).
+//   convp = {conv_f, conv_f+1}, crp = c_r pair, ccp = 1/(sig sqrt2) pair, nyp = -(y/(sig sqrt2)) pair
+__device__ __forceinline__ void frame_pair(const u64 convp, const u64 crp, const u64 ccp, const u64 nyp, const u64 coefd,
+                                           const u64 r1d, u64& Gp, u64& sp, u64& zp) {
+    const u64 raw = ffma2r(convp, coefd, fmul2(crp, r1d));
+    float s0, s1;
+    unpack2(raw, s0, s1);
+    s0 = s0 < 0.f ? 1e-6f : s0;
+    s1 = s1 < 0.f ? 1e-6f : s1;
+    sp = pack2(s0, s1);
+    const u64 rsp = pack2(rsqrt_approx(s0), rsqrt_approx(s1));
+    const u64 up = fmul2(ffma2r(sp, ccp, nyp), rsp);          // (s - y) / (sig sqrt(2 s))
+    Gp = ffma2r(up, up, Gp);                                   // (y-s)^2 / (2 s sig^2)
+    zp = fmul2(fmul2(sp, rsp), ccp);
+}
 
-// log2 of prod_t s_t (1 - erfc(z_t)/2)^2 over up to 4 frames; the erfc factor is skipped
-// warp-uniformly when every lane's z >= Z_CUT (its value never depends on neighbours)
-template <int N>
-__device__ __forceinline__ float trunc_log2(const float (&sv)[4], const float (&zv)[4]) {
-    float zmin = zv[0];
+// log2 of prod_t s_t (1 - erfc(z_t)/2)^2 over NP frame pairs.  The erfc factor is skipped
+// warp-uniformly when every lane has z >= Z_CUT; whether it applies to a given element depends
+// on that element's z alone (branch-free select), never on neighbouring lanes.
+template <int NP>
+__device__ __forceinline__ float trunc_log2(const u64 (&sp)[2], const u64 (&zp)[2]) {
+    float sv[4], zv[4];
 #pragma unroll
-    for (int u = 1; u < N; u++) zmin = fminf(zmin, zv[u]);
-    float pr = sv[0];
+    for (int q = 0; q < NP; q++) { unpack2(sp[q], sv[2 * q], sv[2 * q + 1]); unpack2(zp[q], zv[2 * q], zv[2 * q + 1]); }
+    float zmin = fminf(zv[0], zv[1]);
+    if (NP == 2) zmin = fminf(zmin, fminf(zv[2], zv[3]));
+    float pr;
     if (__any_sync(0xffffffffu, !(zmin >= Z_CUT))) {   // NaN -> evaluate
         pr = 1.f;
 #pragma unroll
-        for (int u = 0; u < N; u++) {
-            const float gsel = (zv[u] >= Z_CUT) ? 1.f : (1.f - half_erfc(zv[u]));
-            pr *= sv[u] * gsel * gsel;
+        for (int u = 0; u < 2 * NP; u++) {
+            const float h = half_erfc(zv[u]);
+            float hm;
+            asm("{ .reg .pred p; setp.lt.f32 p, %1, %2; selp.f32 %0, %3, 0f00000000, p; }"
+                : "=f"(hm) : "f"(zv[u]), "f"(Z_CUT), "f"(h));
+            hm = (zv[u] != zv[u]) ? zv[u] : hm;                // keep NaN
+            const float g = 1.f - hm;
+            pr *= sv[u] * g * g;
         }
     } else {
-#pragma unroll
-        for (int u = 1; u < N; u++) pr *= sv[u];
+        pr = sv[0] * sv[1];
+        if (NP == 2) pr *= sv[2] * sv[3];
     }
     return lg2_approx(pr);
 }
@@ -226,7 +249,8 @@ __device__ __noinline__ float3 eval3(const int l16, const float d0, const float 
     const float k2p = sCr[K2P_SLOT];
     // rotating per-item registers: slot 0 is the item being processed by the likelihood loop
     float na0, na1, na2, coef0, coef1, coef2, r10 = a0, r11 = a1, r12 = a2;
-    float G0 = 0.f, G1 = 0.f, G2 = 0.f, S0 = 0.f, S1 = 0.f, S2 = 0.f;
+    u64 G0 = 0ull, G1 = 0ull, G2 = 0ull;   // Gaussian term, packed partial sums (even / odd frames)
+    float S0 = 0.f, S1 = 0.f, S2 = 0.f;
     {
         const float k20 = k2p * a0, k21 = k2p * a1, k22 = k2p * a2;   // kinetic_model.py:153
         const float k2a0 = k20 / d0, k2a1 = k21 / d1, k2a2 = k22 / d2; // :154
@@ -278,54 +302,56 @@ __device__ __noinline__ float3 eval3(const int l16, const float d0, const float 
         const float* crb = sCr + blk * RB;
 #pragma unroll 1
         for (int it = 0; it < K; it++) {
-            const float4* y4 = reinterpret_cast<const float4*>(sYcc + rowoff0 + blk * RSTRIDE);
-            const float4* c4 = reinterpret_cast<const float4*>(sCc + rowoff0 + blk * RSTRIDE);
-            float cv[RSTRIDE], yv[RSTRIDE], conv[RB];
-#pragma unroll
-            for (int v = 0; v < RSTRIDE / 4; v++) {
-                const float4 a = c4[v], b = y4[v];
-                cv[4 * v] = a.x; cv[4 * v + 1] = a.y; cv[4 * v + 2] = a.z; cv[4 * v + 3] = a.w;
-                yv[4 * v] = b.x; yv[4 * v + 1] = b.y; yv[4 * v + 2] = b.z; yv[4 * v + 3] = b.w;
-            }
-#pragma unroll
-            for (int p = 0; p < NPAIR; p++) unpack2(acc0[p], conv[2 * p], conv[2 * p + 1]);
+            const float* yrow = sYcc + rowoff0 + blk * RSTRIDE;
+            const float* crow = sCc + rowoff0 + blk * RSTRIDE;
+            const u64 coefd = pack2(coef0, coef0), r1d = pack2(r10, r10);
             if (tac_out != nullptr) {   // parity hook only (warp-uniform): the unclamped TAC
 #pragma unroll
-                for (int u = 0; u < RB; u++) tac_out[it * NT + blk * RB + u] = fmaf(coef0, conv[u], r10 * crb[u]);
+                for (int pq = 0; pq < NPAIR; pq++) {
+                    float c0, c1;
+                    unpack2(acc0[pq], c0, c1);
+                    tac_out[it * NT + blk * RB + 2 * pq] = fmaf(coef0, c0, r10 * crb[2 * pq]);
+                    tac_out[it * NT + blk * RB + 2 * pq + 1] = fmaf(coef0, c1, r10 * crb[2 * pq + 1]);
+                }
             }
 #pragma unroll
-            for (int g = 0; g < 4; g++) {
-                float sv[4], zv[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int f = 4 * g + u;
-                    PETMH_FRAME(conv[f], crb[f], cv[f], yv[f], sv[u], zv[u])
+            for (int g = 0; g < 5; g++) {
+                u64 sp[2], zp[2];
+                if (g < 4) {
+                    const float4 cv = *reinterpret_cast<const float4*>(crow + 4 * g);
+                    const float4 yv = *reinterpret_cast<const float4*>(yrow + 4 * g);
+                    const float2 ca = *reinterpret_cast<const float2*>(crb + 4 * g);
+                    const float2 cb = *reinterpret_cast<const float2*>(crb + 4 * g + 2);
+                    frame_pair(acc0[2 * g], pack2(ca.x, ca.y), pack2(cv.x, cv.y), pack2(yv.x, yv.y), coefd, r1d, G0, sp[0], zp[0]);
+                    frame_pair(acc0[2 * g + 1], pack2(cb.x, cb.y), pack2(cv.z, cv.w), pack2(yv.z, yv.w), coefd, r1d, G0, sp[1], zp[1]);
+                    S0 += trunc_log2<2>(sp, zp);
+                } else {
+                    const float2 cv = *reinterpret_cast<const float2*>(crow + 16);
+                    const float2 yv = *reinterpret_cast<const float2*>(yrow + 16);
+                    const float2 ca = *reinterpret_cast<const float2*>(crb + 16);
+                    frame_pair(acc0[8], pack2(ca.x, ca.y), pack2(cv.x, cv.y), pack2(yv.x, yv.y), coefd, r1d, G0, sp[0], zp[0]);
+                    sp[1] = zp[1] = 0ull;
+                    S0 += trunc_log2<1>(sp, zp);
                 }
-                S0 += trunc_log2<4>(sv, zv);
-            }
-            {
-                float sv[4], zv[4];
-#pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    const int f = 16 + u;
-                    PETMH_FRAME(conv[f], crb[f], cv[f], yv[f], sv[u], zv[u])
-                }
-                S0 += trunc_log2<2>(sv, zv);
             }
             // rotate item registers: (0,1,2) <- (1,2,0)
 #pragma unroll
-            for (int p = 0; p < NPAIR; p++) { const u64 t_ = acc0[p]; acc0[p] = acc1[p]; acc1[p] = acc2[p]; acc2[p] = t_; }
+            for (int pq = 0; pq < NPAIR; pq++) { const u64 t_ = acc0[pq]; acc0[pq] = acc1[pq]; acc1[pq] = acc2[pq]; acc2[pq] = t_; }
             { const float t_ = coef0; coef0 = coef1; coef1 = coef2; coef2 = t_; }
             { const float t_ = r10; r10 = r11; r11 = r12; r12 = t_; }
-            { const float t_ = G0; G0 = G1; G1 = G2; G2 = t_; }
+            { const u64 t_ = G0; G0 = G1; G1 = G2; G2 = t_; }
             { const float t_ = S0; S0 = S1; S1 = S2; S2 = t_; }
             { const int t_ = rowoff0; rowoff0 = rowoff1; rowoff1 = rowoff2; rowoff2 = t_; }
         }
     }
     const unsigned char* bad = smem + SM_BAD;
-    const float v0 = -G0 - 0.34657359027997264f * S0;   // -(ln 2)/2 * log2(prod)
-    const float v1 = -G1 - 0.34657359027997264f * S1;
-    const float v2 = -G2 - 0.34657359027997264f * S2;
+    float ga, gb;
+    unpack2(G0, ga, gb);
+    const float v0 = -(ga + gb) - 0.34657359027997264f * S0;   // -(ln 2)/2 * log2(prod)
+    unpack2(G1, ga, gb);
+    const float v1 = -(ga + gb) - 0.34657359027997264f * S1;
+    unpack2(G2, ga, gb);
+    const float v2 = -(ga + gb) - 0.34657359027997264f * S2;
     return make_float3(bad[l16] ? -INFINITY : v0, bad[l16 + 16] ? -INFINITY : v1, bad[l16 + 32] ? -INFINITY : v2);
 }
 
@@ -390,7 +416,7 @@ __device__ __forceinline__ void load_tac_image(const SweepParams& p, int tac, un
         if (u < RB) {
             c = p.cc[r * NT + j];
             const float yv = y[r * NT + j];
-            yc = yv * c;
+            yc = -(yv * c);   // stored negated: (s - y)/(sig sqrt2) = fma(s, cc, -y cc)
             if (yv < 0.f) sBad[r] = 1;   // benign race: all writers store 1
         }
         sCc[i] = c;
