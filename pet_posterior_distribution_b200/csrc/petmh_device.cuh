@@ -88,7 +88,9 @@ struct SweepParams {
 
 // frame end time (minutes) of each active column of M.  One frame grid per process:
 // petmh_set_frames refuses a second, different grid while it is loaded.
-__constant__ float c_tcol[NCOL];
+__constant__ float c_tcol[NCOL + 3];   // (+3: the pipelined M.e loop computes exponentials up to 2 columns ahead)
+// triangle-aware column phases of the M.e loop (tools/gen_schedule.py)
+__constant__ int c_cend[PETMH_NBLK][PETMH_RB / 2] = PETMH_CEND;
 
 // ------------------------------------------------------------------------------------
 // small PTX helpers
@@ -192,6 +194,9 @@ constexpr int K2P_SLOT = 60;
 // is only non-null in the parity hook.
 // ------------------------------------------------------------------------------------
 constexpr int K = SLOTS;
+#ifndef PETMH_TRIANGLE
+#define PETMH_TRIANGLE 0
+#endif
 
 // Two consecutive frames of one item in packed fp32x2 arithmetic (FMUL2 / FFMA2):
 // TAC assembly (kinetic_model.py:157-158), clamp (mcmc.py:152), Gaussian term, z = sqrt(s)/(sig sqrt2).
@@ -267,37 +272,72 @@ __device__ __noinline__ float3 eval3(const int l16, const float d0, const float 
 
 #pragma unroll 1
     for (int blk = 0; blk < NBLK; blk++) {
-        const int ncols = blk == 0 ? 11 : (blk == 1 ? 28 : 45);         // PETMH_NCB
         const float4* Mp = reinterpret_cast<const float4*>(sM + (blk == 0 ? 0 : (blk == 1 ? 220 : 780)));   // PETMH_MOFF
         u64 acc0[NPAIR], acc1[NPAIR], acc2[NPAIR];
 #pragma unroll
         for (int p = 0; p < NPAIR; p++) acc0[p] = acc1[p] = acc2[p] = 0ull;
         // ---- conv rows of this block: acc += M[:, c] * e_c over the block's active columns ----
-        // software pipeline: the next column's 5 chunks are in flight while this one is consumed
-        float4 mc0 = Mp[0], mc1 = Mp[1], mc2 = Mp[2], mc3 = Mp[3];
-        float2 mc4 = *reinterpret_cast<const float2*>(Mp + 4);
-#pragma unroll 2
-        for (int c = 0; c < ncols; c++) {
-            Mp += RSTRIDE / 4;   // (the read past the last column stays inside shared memory)
-            const float4 mn0 = Mp[0], mn1 = Mp[1], mn2 = Mp[2], mn3 = Mp[3];
-            const float2 mn4 = *reinterpret_cast<const float2*>(Mp + 4);
-            const float tc = c_tcol[c];
-            const float e0 = ex2_approx(na0 * tc), e1 = ex2_approx(na1 * tc), e2 = ex2_approx(na2 * tc);
-            const u64 ed0 = pack2(e0, e0), ed1 = pack2(e1, e1), ed2 = pack2(e2, e2);   // FFMA2 scalar-broadcast operand
-#define PETMH_CH(v, m)                                                                                          \
-    {                                                                                                           \
-        const u64 m01 = pack2(m.x, m.y), m23 = pack2(m.z, m.w);                                                 \
-        ffma2(acc0[2 * v], m01, ed0); ffma2(acc1[2 * v], m01, ed1); ffma2(acc2[2 * v], m01, ed2);               \
-        ffma2(acc0[2 * v + 1], m23, ed0); ffma2(acc1[2 * v + 1], m23, ed1); ffma2(acc2[2 * v + 1], m23, ed2);   \
+        // Column c touches only row pairs >= z(c) (the operator is a triangle): phase z runs the columns
+        // [cend[z-1], cend[z]) over pairs z..8.  Phase 0 (the bulk) is software-pipelined with two
+        // register buffers (ping-pong, no copies); FFMA2 takes the exponential as scalar-broadcast operand.
+#define PETMH_EXPS(E, c_)                                                                                        \
+    {                                                                                                            \
+        const float tc_ = c_tcol[c_];                                                                            \
+        E##0 = ex2_approx(na0 * tc_); E##1 = ex2_approx(na1 * tc_); E##2 = ex2_approx(na2 * tc_);                \
     }
-            PETMH_CH(0, mc0) PETMH_CH(1, mc1) PETMH_CH(2, mc2) PETMH_CH(3, mc3)
-#undef PETMH_CH
-            {
-                const u64 m01 = pack2(mc4.x, mc4.y);
-                ffma2(acc0[8], m01, ed0); ffma2(acc1[8], m01, ed1); ffma2(acc2[8], m01, ed2);
+#define PETMH_PAIR(E, pq, m01)                                                                                   \
+    { ffma2(acc0[pq], m01, pack2(E##0, E##0)); ffma2(acc1[pq], m01, pack2(E##1, E##1)); ffma2(acc2[pq], m01, pack2(E##2, E##2)); }
+#define PETMH_CH(E, v, m)                                                                                        \
+    { PETMH_PAIR(E, 2 * (v), pack2(m.x, m.y)) PETMH_PAIR(E, 2 * (v) + 1, pack2(m.z, m.w)) }
+#define PETMH_LOADCOL(B, ptr)                                                                                    \
+    B##0 = (ptr)[0]; B##1 = (ptr)[1]; B##2 = (ptr)[2]; B##3 = (ptr)[3]; B##4 = *reinterpret_cast<const float2*>((ptr) + 4);
+#define PETMH_FULLCOL(B, E)                                                                                      \
+    { PETMH_CH(E, 0, B##0) PETMH_CH(E, 1, B##1) PETMH_CH(E, 2, B##2) PETMH_CH(E, 3, B##3) PETMH_PAIR(E, 8, pack2((B##4).x, (B##4).y)) }
+        {
+            const int n0 = c_cend[blk][PETMH_TRIANGLE ? 0 : 8];
+            float4 ma0, ma1, ma2, ma3, mb0, mb1, mb2, mb3;
+            float2 ma4, mb4;
+            float ea0, ea1, ea2, eb0, eb1, eb2;
+            PETMH_LOADCOL(ma, Mp)
+            PETMH_EXPS(ea, 0)
+            int c = 0;
+#pragma unroll 1
+            for (; c + 1 < n0; c += 2) {
+                PETMH_LOADCOL(mb, Mp + (RSTRIDE / 4))
+                PETMH_EXPS(eb, c + 1)
+                PETMH_FULLCOL(ma, ea)
+                PETMH_LOADCOL(ma, Mp + 2 * (RSTRIDE / 4))   // (reads / exponentials past the block's last column are harmless)
+                PETMH_EXPS(ea, c + 2)
+                PETMH_FULLCOL(mb, eb)
+                Mp += 2 * (RSTRIDE / 4);
             }
-            mc0 = mn0; mc1 = mn1; mc2 = mn2; mc3 = mn3; mc4 = mn4;
+            if (c < n0) {
+                PETMH_FULLCOL(ma, ea)
+                Mp += RSTRIDE / 4;
+            }
         }
+        // partial columns: pairs z..8 only
+#define PETMH_PHASE(ZP)                                                                                           \
+    {                                                                                                            \
+        const int ce_ = c_cend[blk][ZP];                                                                          \
+        _Pragma("unroll 1") for (int c = c_cend[blk][(ZP) - 1]; c < ce_; c++, Mp += RSTRIDE / 4) {                \
+            float ep0, ep1, ep2; PETMH_EXPS(ep, c)                                                                                        \
+            if ((ZP) <= 1) { const float4 m = Mp[0]; if ((ZP) <= 0) PETMH_PAIR(ep, 0, pack2(m.x, m.y)) PETMH_PAIR(ep, 1, pack2(m.z, m.w)) } \
+            if ((ZP) <= 3) { const float4 m = Mp[1]; if ((ZP) <= 2) PETMH_PAIR(ep, 2, pack2(m.x, m.y)) PETMH_PAIR(ep, 3, pack2(m.z, m.w)) } \
+            if ((ZP) <= 5) { const float4 m = Mp[2]; if ((ZP) <= 4) PETMH_PAIR(ep, 4, pack2(m.x, m.y)) PETMH_PAIR(ep, 5, pack2(m.z, m.w)) } \
+            if ((ZP) <= 7) { const float4 m = Mp[3]; if ((ZP) <= 6) PETMH_PAIR(ep, 6, pack2(m.x, m.y)) PETMH_PAIR(ep, 7, pack2(m.z, m.w)) } \
+            { const float2 m = *reinterpret_cast<const float2*>(Mp + 4); PETMH_PAIR(ep, 8, pack2(m.x, m.y)) }        \
+        }                                                                                                        \
+    }
+#if PETMH_TRIANGLE
+        PETMH_PHASE(1) PETMH_PHASE(2) PETMH_PHASE(3) PETMH_PHASE(4) PETMH_PHASE(5) PETMH_PHASE(6) PETMH_PHASE(7) PETMH_PHASE(8)
+#endif
+#undef PETMH_PHASE
+#undef PETMH_FULLCOL
+#undef PETMH_LOADCOL
+#undef PETMH_CH
+#undef PETMH_PAIR
+#undef PETMH_EXPS
         // ---- likelihood of the block's 18 frames, one item per iteration (registers rotate) ----
         const float* crb = sCr + blk * RB;
 #pragma unroll 1
