@@ -293,7 +293,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tacs-per-gpu", type=int, default=131072)
     ap.add_argument("--base-tacs", type=int, default=1024)
-    ap.add_argument("--sweeps", type=int, default=25)
+    ap.add_argument("--sweeps", type=int, default=50)
     ap.add_argument("--tune", type=int, default=1500)
     ap.add_argument("--cpu-sweeps", type=int, default=40)
     ap.add_argument("--ref-sweeps", type=int, default=8)
