@@ -40,7 +40,8 @@ struct petmh_handle {
     double* d_cref = nullptr;
     float* d_k2p = nullptr;
     // state
-    float *d_q = nullptr, *d_scale = nullptr, *d_mom = nullptr, *d_draws = nullptr;
+    float *d_q = nullptr, *d_scale = nullptr, *d_mom = nullptr, *d_draws = nullptr, *d_mom_first = nullptr;
+    float4* d_momw = nullptr;
     uint8_t* d_cnt = nullptr;
     uint32_t* d_nacc = nullptr;
     // schedule
@@ -228,6 +229,8 @@ extern "C" int petmh_create(const petmh_cfg* cfg, petmh_t** out) {
     CUC(cudaMalloc(&h->d_cnt, NC * 96));
     CUC(cudaMalloc(&h->d_nacc, NC * 96 * sizeof(uint32_t)));
     CUC(cudaMalloc(&h->d_mom, NC * 96 * 6 * sizeof(float)));
+    CUC(cudaMalloc(&h->d_momw, NC * 96 * sizeof(float4)));
+    CUC(cudaMalloc(&h->d_mom_first, NC * 96 * sizeof(float)));
     if (cfg->max_draws > 0) CUC(cudaMalloc(&h->d_draws, NC * (size_t)cfg->max_draws * 96 * sizeof(float)));
     CUC(cudaMalloc(&h->d_scratch, (48 * NT + 256) * sizeof(float)));
     CUC(cudaMalloc(&h->d_scratch64, NT * NT * sizeof(double)));
@@ -243,7 +246,7 @@ extern "C" void petmh_destroy(petmh_t* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     void* bufs[] = {h->d_ft, h->d_P, h->d_mu, h->d_cc, h->d_y, h->d_cref, h->d_k2p, h->d_q, h->d_scale,
-                    h->d_cnt, h->d_nacc, h->d_mom, h->d_draws, h->d_scratch, h->d_scratch64};
+                    h->d_cnt, h->d_nacc, h->d_mom, h->d_draws, h->d_scratch, h->d_scratch64, h->d_momw, h->d_mom_first};
     for (void* b : bufs) if (b) cudaFree(b);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -406,6 +409,8 @@ static SweepParams base_params(petmh_t* h) {
     p.draws = h->d_draws;
     p.mom = h->d_mom;
     p.nacc = h->d_nacc;
+    p.momw = h->d_momw;
+    p.mom_first = h->d_mom_first;
     p.max_draws = h->cfg.max_draws;
     p.n_tacs = h->n_tac;
     p.n_chains = h->cfg.n_chains;

@@ -71,6 +71,8 @@ struct SweepParams {
     float* mom;             // [S*C][2 halves][96][3]: mean - mu, M2, lag-1 co-moment (Chan-merged per launch)
     int mom_n_before;       // draws already merged into this half
     uint32_t* nacc;         // [S*C][96] accepted moves in draw sweeps
+    float4* momw;           // [S*C][96] per-launch scratch: sum, sumsq, lag-1 products, previous draw (of q - ref)
+    float* mom_first;       // [S*C][96] first draw of the launch (q - ref)
     int max_draws;          // capacity (stored draws per chain)
     int mom_half;           // which half this launch accumulates into
     int n_tacs, n_chains;
@@ -182,7 +184,8 @@ constexpr int SM_CR = SM_M + MPACK * 4;                   // float [64]      ref
 constexpr int SM_YCC = SM_CR + 64 * 4;                    // float [48][YS]  -(y * cc)
 constexpr int SM_CC = SM_YCC + 48 * YS * 4;               // float [48][YS]  1/(sigma sqrt2)
 constexpr int SM_BAD = SM_CC + 48 * YS * 4;               // uchar [48] (+pad) 1 if any y < 0
-constexpr int SM_STATE = SM_BAD + 64;                     // float [ST_WORDS][nthreads] per-thread chain state
+constexpr int SM_P = SM_BAD + 64;                         // double [2][48][48] prior precision matrices
+constexpr int SM_STATE = SM_P + 2 * 48 * 48 * 8;          // float [ST_WORDS][nthreads] per-thread chain state
 constexpr int K2P_SLOT = 60;
 
 // ------------------------------------------------------------------------------------
@@ -441,6 +444,10 @@ __device__ __forceinline__ void load_tac_image(const SweepParams& p, int tac, un
     float* sYcc = reinterpret_cast<float*>(smem + SM_YCC);
     float* sCc = reinterpret_cast<float*>(smem + SM_CC);
     unsigned char* sBad = smem + SM_BAD;
+    {
+        double* sPd = reinterpret_cast<double*>(smem + SM_P);
+        for (int i = tid; i < 2 * 48 * 48; i += nthr) sPd[i] = p.P[i];
+    }
     const double* cref = p.cref + (size_t)tac * NT;
     build_crs(p.ft, cref, sCrs, tid, nthr);
     for (int i = tid; i < 64; i += nthr) sCr[i] = i < NT ? (float)cref[i] : (i == K2P_SLOT ? p.k2p[tac] : 0.f);
@@ -483,10 +490,11 @@ __device__ __forceinline__ float tune_factor(int c) {
 // every access is conflict-free) and only the current block's copy is in registers:
 //   block b (b = 0 DVR, 1 R1), words b*18 + ...: q[3] f32, scale[3] f32, cnt[3] i32,
 //   nacc[3] u32, r[3] f64 (6 words)
-//   words 36..71: per coordinate c = b*3+slot: sum, sumsq, lag, ref, first, prev (f32,
-//   running moments of q - ref over this launch's draw sweeps)
+// The running moments of this launch's draw sweeps (sum, sumsq, lag-1 products, previous draw of
+// q - ref, ref = q at launch start) are read-modify-written once per sweep in a global scratch
+// (float4 per coordinate, L2-resident) so that shared memory can hold the fp64 prior precision.
 // ------------------------------------------------------------------------------------
-constexpr int ST_BLOCK = 18, ST_MOM = 36, ST_WORDS = 72;
+constexpr int ST_BLOCK = 18, ST_WORDS = 36;
 __host__ __device__ constexpr int smem_bytes(int nthreads) { return SM_STATE + ST_WORDS * 4 * nthreads; }
 
 // VARIANT 0: 256-thread CTAs, 2 CTAs/SM (128-register cap); VARIANT 1: 128-thread CTAs, 3 CTAs/SM (168).
@@ -536,14 +544,12 @@ __global__ void __launch_bounds__(VARIANT == 0 ? 256 : 128, VARIANT == 0 ? 2 : 3
                 ST_F(b * ST_BLOCK + 3 + s) = sc;
                 ST_I(b * ST_BLOCK + 6 + s) = cn;
                 ST_U(b * ST_BLOCK + 9 + s) = 0u;
-                const int c = b * SLOTS + s;
-                ST_F(ST_MOM + c * 6 + 0) = 0.f; ST_F(ST_MOM + c * 6 + 1) = 0.f; ST_F(ST_MOM + c * 6 + 2) = 0.f;
-                ST_F(ST_MOM + c * 6 + 3) = qv;  ST_F(ST_MOM + c * 6 + 4) = 0.f; ST_F(ST_MOM + c * 6 + 5) = 0.f;
+                if (!TAPED && active) p.momw[o] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll 1
         for (int b = 0; b < 2; b++) {
             double r0 = 0.0, r1 = 0.0, r2 = 0.0;
-            const double* Pb = p.P + b * 48 * 48 + l16;
+            const double* Pb = reinterpret_cast<const double*>(smem + SM_P) + b * 48 * 48 + l16;
 #pragma unroll 1
             for (int j = 0; j < 48; j++) {
                 const float mine = (j >> 4) == 0 ? q0[b][0] : ((j >> 4) == 1 ? q0[b][1] : q0[b][2]);
@@ -611,7 +617,7 @@ __global__ void __launch_bounds__(VARIANT == 0 ? 256 : 128, VARIANT == 0 ? 2 : 3
             }
             // ---- phase B: resolve visits in key order ----
             // accept iff logu < dll - (d r + d^2 Pii / 2)  <=>  pre + d r < 0;  non-finite dll never accepts
-            const double* Pl = p.P + b * 48 * 48 + l16;               // P[b][.][l16 + 16 s]
+            const double* Pl = reinterpret_cast<const double*>(smem + SM_P) + b * 48 * 48 + l16;   // P[b][.][l16 + 16 s]
             double d[SLOTS], pre[SLOTS], r[SLOTS];
 #pragma unroll
             for (int s = 0; s < SLOTS; s++) {
@@ -684,17 +690,21 @@ __global__ void __launch_bounds__(VARIANT == 0 ? 256 : 128, VARIANT == 0 ? 2 : 3
         if (!tuning) {
             const int di = sweep - p.tune_until;
             const bool store = !TAPED && p.draws != nullptr && active && (di % p.thin) == 0 && (di / p.thin) < p.max_draws;
+            if (!TAPED && active) {
 #pragma unroll
-            for (int c = 0; c < 2 * SLOTS; c++) {
-                const float qv = ST_F((c / SLOTS) * ST_BLOCK + (c % SLOTS));
-                const float x = qv - ST_F(ST_MOM + c * 6 + 3);
-                ST_F(ST_MOM + c * 6 + 0) += x;
-                ST_F(ST_MOM + c * 6 + 1) = fmaf(x, x, ST_F(ST_MOM + c * 6 + 1));
-                if (have_prev) ST_F(ST_MOM + c * 6 + 2) = fmaf(x, ST_F(ST_MOM + c * 6 + 5), ST_F(ST_MOM + c * 6 + 2));
-                else ST_F(ST_MOM + c * 6 + 4) = x;                    // first draw of this launch
-                ST_F(ST_MOM + c * 6 + 5) = x;
-                if (store)
-                    p.draws[(cg * p.max_draws + di / p.thin) * 96 + (c / SLOTS) * 48 + (c % SLOTS) * 16 + l16] = qv;
+                for (int c = 0; c < 2 * SLOTS; c++) {
+                    const size_t o = cg * 96 + (c / SLOTS) * 48 + (c % SLOTS) * 16 + l16;
+                    const float qv = ST_F((c / SLOTS) * ST_BLOCK + (c % SLOTS));
+                    const float x = qv - p.q[o];                      // ref = q at launch start (p.q is rewritten in the epilogue only)
+                    float4 m = p.momw[o];
+                    m.x += x;
+                    m.y = fmaf(x, x, m.y);
+                    if (have_prev) m.z = fmaf(x, m.w, m.z);
+                    else p.mom_first[o] = x;                          // first draw of this launch
+                    m.w = x;
+                    p.momw[o] = m;
+                    if (store) p.draws[(cg * p.max_draws + di / p.thin) * 96 + (c / SLOTS) * 48 + (c % SLOTS) * 16 + l16] = qv;
+                }
             }
             have_prev = true;
         }
@@ -710,15 +720,17 @@ __global__ void __launch_bounds__(VARIANT == 0 ? 256 : 128, VARIANT == 0 ? 2 : 3
                 p.scale[(size_t)chain * 96 + b * 48 + i] = ST_F(b * ST_BLOCK + 3 + s);   // scale_out
                 continue;
             }
+            const float qref = p.q[o];
             p.q[o] = ST_F(b * ST_BLOCK + s);
             p.scale[o] = ST_F(b * ST_BLOCK + 3 + s);
             p.cnt[o] = (uint8_t)ST_I(b * ST_BLOCK + 6 + s);
             p.nacc[o] += ST_U(b * ST_BLOCK + 9 + s);
             if (nb > 0) {
                 float* mo = p.mom + ((cg * 2 + p.mom_half) * 96 + b * 48 + i) * 3;
-                const double sum = ST_F(ST_MOM + c * 6 + 0), sq = ST_F(ST_MOM + c * 6 + 1), lag = ST_F(ST_MOM + c * 6 + 2);
-                const double ref = (double)ST_F(ST_MOM + c * 6 + 3) - p.mu[b * 48 + i];   // launch reference about mu
-                const double x0 = ST_F(ST_MOM + c * 6 + 4), xl = ST_F(ST_MOM + c * 6 + 5);
+                const float4 mw = p.momw[o];
+                const double sum = mw.x, sq = mw.y, lag = mw.z;
+                const double ref = (double)qref - p.mu[b * 48 + i];                    // launch reference about mu
+                const double x0 = p.mom_first[o], xl = mw.w;
                 const double mean_r = sum / nb;                                        // about ref
                 const double M2_b = sq - sum * mean_r;
                 // sum_t (x_t - m)(x_{t-1} - m), t = 1..nb-1, exactly
