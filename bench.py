@@ -219,6 +219,26 @@ def run_b200(args):
     summ = out_pin.numpy()
     ok = bool(np.isfinite(summ[..., 0]).all() and np.isfinite(summ[..., 1]).all())
 
+    # ---- BASELINE configs[1]: one test TAC, 48 ROIs x 64 chains, full posterior incl. diagnostics (rank 0) ----
+    cfg2 = None
+    if rank == 0:
+        try:
+            n_sw_t, n_sw_d = 4000, 2000
+            with MHSampler(n_chains=64, max_tacs=1, max_draws=n_sw_d, seed=11, device=local) as s2:
+                s2.set_frames(t, dtv)
+                s2.set_prior(prior["mu_DVR"], prior["Cov_DVR"], prior["mu_R1"], prior["Cov_R1"])
+                s2.set_data(yb[:1], cb[:1], k_pin.numpy()[:1], sig)
+                t2 = time.perf_counter()
+                s2.run(draws=n_sw_d, tune=n_sw_t)
+                sm2 = s2.summary()
+                dt2 = time.perf_counter() - t2
+            cfg2 = {"workload": "BASELINE configs[1]: 1 TAC x 48 ROIs x 64 chains, %d tune + %d draws, rank-normalised R-hat/ESS on GPU" % (n_sw_t, n_sw_d),
+                    "seconds": dt2, "chain_steps_per_s": 64 * 96 * (n_sw_t + n_sw_d) / dt2,
+                    "seconds_extrapolated_to_40000_tune_20000_draws": dt2 * 10.0,
+                    "rhat_max": float(np.nanmax(sm2[0, :, 5])), "ess_bulk_min": float(np.nanmin(sm2[0, :, 3]))}
+        except Exception as e:      # pragma: no cover
+            cfg2 = {"error": repr(e)}
+
     tt = torch.tensor([dev_ms * 1e-3, wall, e2e_wall], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -265,7 +285,7 @@ def run_b200(args):
                        "tacs_per_gpu": S, "chains_per_tac": C, "sweeps_per_step": SW, "chain_steps_per_step": steps_per_step,
                        "l2_policy": "per-step working set (inputs+state %.1f GB) >> 126 MB L2" % ((S * 10588 + S * C * 3500) / 1e9),
                        "sec_per_48roi_posterior_60000_sweeps_amortised": 60000 * 96 * C / (value / world) ,
-                       "summary_finite": ok},
+                       "summary_finite": ok, "sec_per_48roi_posterior": cfg2},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "chain-steps/s", "h2d_bytes_per_step": int(S * (48 * 54 + 54 + 1) * 4) * world,
                     "d2h_bytes_per_step": int(S * 96 * 8 * 4) * world,

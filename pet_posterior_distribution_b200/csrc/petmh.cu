@@ -42,6 +42,7 @@ struct petmh_handle {
     // state
     float *d_q = nullptr, *d_scale = nullptr, *d_mom = nullptr, *d_draws = nullptr, *d_mom_first = nullptr;
     float4* d_momw = nullptr;
+    float* d_summary = nullptr;   // [max_tacs][96][8], allocated on first petmh_get_summary
     uint8_t* d_cnt = nullptr;
     uint32_t* d_nacc = nullptr;
     // schedule
@@ -246,7 +247,7 @@ extern "C" void petmh_destroy(petmh_t* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     void* bufs[] = {h->d_ft, h->d_P, h->d_mu, h->d_cc, h->d_y, h->d_cref, h->d_k2p, h->d_q, h->d_scale,
-                    h->d_cnt, h->d_nacc, h->d_mom, h->d_draws, h->d_scratch, h->d_scratch64, h->d_momw, h->d_mom_first};
+                    h->d_cnt, h->d_nacc, h->d_mom, h->d_draws, h->d_scratch, h->d_scratch64, h->d_momw, h->d_mom_first, h->d_summary};
     for (void* b : bufs) if (b) cudaFree(b);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -719,14 +720,10 @@ extern "C" int petmh_get_summary(petmh_t* h, float* out) {
     if (!h || !out) return fail(h, PETMH_EINVAL, "null argument");
     CU(cudaSetDevice(h->cfg.device));
     const size_t n = (size_t)h->n_tac * 96 * PETMH_N_STATS;
-    float* d = nullptr;
-    CU(cudaMalloc(&d, n * sizeof(float)));
-    int rc = petmh_summary_device(h, d, nullptr);
-    if (rc == PETMH_OK) {
-        cudaError_t e = cudaMemcpyAsync(out, d, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-        if (e != cudaSuccess) rc = fail(h, PETMH_ECUDA, "summary copy failed: %s", cudaGetErrorString(e));
-    }
-    cudaFree(d);
-    return rc;
+    if (!h->d_summary) CU(cudaMalloc(&h->d_summary, (size_t)h->cfg.max_tacs * 96 * PETMH_N_STATS * sizeof(float)));
+    int rc = petmh_summary_device(h, h->d_summary, nullptr);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out, h->d_summary, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return PETMH_OK;
 }
