@@ -235,8 +235,9 @@ extern "C" int petmh_create(const petmh_cfg* cfg, petmh_t** out) {
     if (cfg->max_draws > 0) CUC(cudaMalloc(&h->d_draws, NC * (size_t)cfg->max_draws * 96 * sizeof(float)));
     CUC(cudaMalloc(&h->d_scratch, (48 * NT + 256) * sizeof(float)));
     CUC(cudaMalloc(&h->d_scratch64, NT * NT * sizeof(double)));
-    CUC(cudaFuncSetAttribute(mh_sweep_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(256)));
-    CUC(cudaFuncSetAttribute(mh_sweep_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(128)));
+    CUC(cudaFuncSetAttribute(mh_sweep_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(256)));
+    CUC(cudaFuncSetAttribute(mh_sweep_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(128)));
+    CUC(cudaFuncSetAttribute(mh_sweep_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(256)));
     CUC(cudaFuncSetAttribute(forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_STATE + 32 * SLOTS * NT * 4));
 #undef CUC
     *out = h;
@@ -555,8 +556,8 @@ extern "C" int petmh_advance(petmh_t* h, int n_sweeps) {
         const int half = (drawing && h->sweep >= half_at) ? 1 : 0;
         p.mom_half = half;
         p.mom_n_before = h->mom_n[half];
-        if (h->variant == 0) mh_sweep_kernel<0><<<grid, nthr, smem_bytes(nthr), h->stream>>>(p);
-        else mh_sweep_kernel<1><<<grid, nthr, smem_bytes(nthr), h->stream>>>(p);
+        if (h->variant == 0) mh_sweep_kernel<0, false><<<grid, nthr, smem_bytes(nthr), h->stream>>>(p);
+        else mh_sweep_kernel<1, false><<<grid, nthr, smem_bytes(nthr), h->stream>>>(p);
         CU(cudaGetLastError());
         if (drawing) { h->mom_n[half] += n; h->mom_launches[half] += 1; }
         h->sweep += n;
@@ -610,8 +611,7 @@ extern "C" int petmh_run_taped(petmh_t* h, int tac, int n_tape_chains, int n_swe
     int nthr = std::min(256, (n_tape_chains * 16 + 31) / 32 * 32);
     const int cpc = nthr / 16;
     const unsigned grid = (unsigned)((n_tape_chains + cpc - 1) / cpc);
-    if (h->variant == 0) mh_sweep_kernel<0><<<grid, nthr, smem_bytes(nthr), h->stream>>>(p);
-    else { nthr = std::min(nthr, 128); mh_sweep_kernel<1><<<(unsigned)((n_tape_chains + nthr / 16 - 1) / (nthr / 16)), nthr, smem_bytes(nthr), h->stream>>>(p); }
+    mh_sweep_kernel<0, true><<<grid, nthr, smem_bytes(nthr), h->stream>>>(p);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(draws_out, dd, n * 4, cudaMemcpyDeviceToHost, h->stream));
     if (delta_out) CU(cudaMemcpyAsync(delta_out, ddelta, n * 4, cudaMemcpyDeviceToHost, h->stream));

@@ -237,7 +237,6 @@ __device__ __forceinline__ float trunc_log2(const u64 (&sp)[2], const u64 (&zp)[
             float hm;
             asm("{ .reg .pred p; setp.lt.f32 p, %1, %2; selp.f32 %0, %3, 0f00000000, p; }"
                 : "=f"(hm) : "f"(zv[u]), "f"(Z_CUT), "f"(h));
-            hm = (zv[u] != zv[u]) ? zv[u] : hm;                // keep NaN
             const float g = 1.f - hm;
             pr *= sv[u] * g * g;
         }
@@ -498,11 +497,10 @@ constexpr int ST_BLOCK = 18, ST_WORDS = 36;
 __host__ __device__ constexpr int smem_bytes(int nthreads) { return SM_STATE + ST_WORDS * 4 * nthreads; }
 
 // VARIANT 0: 256-thread CTAs, 2 CTAs/SM (128-register cap); VARIANT 1: 128-thread CTAs, 3 CTAs/SM (168).
-template <int VARIANT>
+template <int VARIANT, bool TAPED>
 __global__ void __launch_bounds__(VARIANT == 0 ? 256 : 128, VARIANT == 0 ? 2 : 3) mh_sweep_kernel(const SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const bool TAPED = p.tape_n != nullptr;
     const int lane = tid & 31, warp = tid >> 5;
     const int half = lane >> 4, l16 = lane & 15;
     const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
