@@ -503,7 +503,6 @@ __global__ void __launch_bounds__(VARIANT == 0 ? 256 : 128, VARIANT == 0 ? 2 : 3
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int half = lane >> 4, l16 = lane & 15;
-    const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
     const int chains_per_cta = nthr >> 4;
     const int groups_per_tac = (p.n_chains + chains_per_cta - 1) / chains_per_cta;
     const int tac = TAPED ? p.tape_tac : (int)(blockIdx.x / groups_per_tac);
@@ -638,7 +637,11 @@ __global__ void __launch_bounds__(VARIANT == 0 ? 256 : 128, VARIANT == 0 ? 2 : 3
 #pragma unroll
                 for (int s = 0; s < SLOTS; s++)
                     if (key[s] > last && fma(d[s], r[s], pre[s]) < 0.0) cand = min(cand, key[s]);
-                const uint32_t win = __reduce_min_sync(hmask, cand);
+                // first accepted coordinate in visit order, per chain (half-warp): two full-warp REDUX.MIN
+                // (uniform results, no divergence) instead of one reduction per half mask
+                const uint32_t w_lo = __reduce_min_sync(0xffffffffu, half ? 0xffffffffu : cand);
+                const uint32_t w_hi = __reduce_min_sync(0xffffffffu, half ? cand : 0xffffffffu);
+                const uint32_t win = half ? w_hi : w_lo;
                 if (TAPED && p.dbg_delta != nullptr && active) {
 #pragma unroll
                     for (int s = 0; s < SLOTS; s++)
@@ -648,12 +651,16 @@ __global__ void __launch_bounds__(VARIANT == 0 ? 256 : 128, VARIANT == 0 ? 2 : 3
                             p.dbg_accept[o] = key[s] == win ? 1 : 0;
                         }
                 }
+                if ((w_lo & w_hi) == 0xffffffffu) break;              // warp-uniform: both chains are done
                 const bool any_win = win != 0xffffffffu;
-                if (!__any_sync(0xffffffffu, any_win)) break;
                 const int wi = (int)(win & 63u);                      // winning coordinate (63 if none)
                 const int ws = wi >> 4;
-                const double dsel = ws == 0 ? d[0] : (ws == 1 ? d[1] : d[2]);
-                const double dw = __shfl_sync(0xffffffffu, dsel, (half << 4) | (wi & 15));
+                // branch-free select of the winner slot's move (both 32-bit halves), then broadcast
+                int dlo = __double2loint(d[0]), dhi = __double2hiint(d[0]);
+                dlo = ws == 1 ? __double2loint(d[1]) : dlo; dhi = ws == 1 ? __double2hiint(d[1]) : dhi;
+                dlo = ws == 2 ? __double2loint(d[2]) : dlo; dhi = ws == 2 ? __double2hiint(d[2]) : dhi;
+                const int src = (half << 4) | (wi & 15);
+                const double dw = __hiloint2double(__shfl_sync(0xffffffffu, dhi, src), __shfl_sync(0xffffffffu, dlo, src));
                 if (any_win) {
                     const double* Pc = Pl + wi * 48;
                     r[0] = fma(Pc[0], dw, r[0]);
