@@ -198,7 +198,7 @@ constexpr int K2P_SLOT = 60;
 // ------------------------------------------------------------------------------------
 constexpr int K = SLOTS;
 #ifndef PETMH_TRIANGLE
-#define PETMH_TRIANGLE 0
+#define PETMH_TRIANGLE 1   // triangle-aware column phases: +2 % measured once the rest of the kernel got leaner
 #endif
 
 // Two consecutive frames of one item in packed fp32x2 arithmetic (FMUL2 / FFMA2):
