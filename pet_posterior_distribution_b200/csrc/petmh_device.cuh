@@ -116,6 +116,11 @@ __device__ __forceinline__ u64 fmul2(u64 a, u64 b) {
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+__device__ __forceinline__ u64 fadd2(u64 a, u64 b) {
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 __device__ __forceinline__ u64 ffma2r(u64 a, u64 b, u64 c) {
     u64 r;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
@@ -218,33 +223,56 @@ __device__ __forceinline__ void frame_pair(const u64 convp, const u64 crp, const
     zp = fmul2(fmul2(sp, rsp), ccp);
 }
 
+// (1 - erfc(z)/2) for a packed pair of z >= 0 (same fit as half_erfc, FFMA2/FMUL2 arithmetic); elements
+// with z >= Z_CUT give exactly 1 (branch-free select on the element's own z).
+__device__ __forceinline__ u64 trunc_factor2(const u64 zp) {
+    float z0, z1;
+    unpack2(zp, z0, z1);
+    const u64 one = pack2(1.0f, 1.0f);
+    const u64 den = ffma2r(zp, pack2(0.389f, 0.389f), one);
+    float d0, d1;
+    unpack2(den, d0, d1);
+    const u64 t = pack2(rcp_approx(d0), rcp_approx(d1));
+    u64 q = pack2(-1.149781880e-01f, -1.149781880e-01f);
+    q = ffma2r(q, t, pack2(4.521313931e-01f, 4.521313931e-01f));
+    q = ffma2r(q, t, pack2(-3.312711738e-01f, -3.312711738e-01f));
+    q = ffma2r(q, t, pack2(3.342878070e-01f, 3.342878070e-01f));
+    q = ffma2r(q, t, pack2(4.196145208e-02f, 4.196145208e-02f));
+    q = ffma2r(q, t, pack2(1.178687081e-01f, 1.178687081e-01f));
+    const u64 arg = fmul2(fmul2(zp, zp), pack2(-1.4426950408889634f, -1.4426950408889634f));
+    float a0, a1;
+    unpack2(arg, a0, a1);
+    const u64 h = fmul2(fmul2(q, t), pack2(ex2_approx(a0), ex2_approx(a1)));
+    float h0, h1, m0, m1;
+    unpack2(h, h0, h1);
+    asm("{ .reg .pred p; setp.lt.f32 p, %1, %2; selp.f32 %0, %3, 0f00000000, p; }" : "=f"(m0) : "f"(z0), "f"(Z_CUT), "f"(h0));
+    asm("{ .reg .pred p; setp.lt.f32 p, %1, %2; selp.f32 %0, %3, 0f00000000, p; }" : "=f"(m1) : "f"(z1), "f"(Z_CUT), "f"(h1));
+    return fadd2(one, pack2(-m0, -m1));
+}
+
 // log2 of prod_t s_t (1 - erfc(z_t)/2)^2 over NP frame pairs.  The erfc factor is skipped
 // warp-uniformly when every lane has z >= Z_CUT; whether it applies to a given element depends
 // on that element's z alone (branch-free select), never on neighbouring lanes.
 template <int NP>
 __device__ __forceinline__ float trunc_log2(const u64 (&sp)[2], const u64 (&zp)[2]) {
-    float sv[4], zv[4];
-#pragma unroll
-    for (int q = 0; q < NP; q++) { unpack2(sp[q], sv[2 * q], sv[2 * q + 1]); unpack2(zp[q], zv[2 * q], zv[2 * q + 1]); }
-    float zmin = fminf(zv[0], zv[1]);
-    if (NP == 2) zmin = fminf(zmin, fminf(zv[2], zv[3]));
-    float pr;
+    float z0, z1, z2, z3;
+    unpack2(zp[0], z0, z1);
+    float zmin = fminf(z0, z1);
+    if (NP == 2) { unpack2(zp[1], z2, z3); zmin = fminf(zmin, fminf(z2, z3)); }
+    u64 prp = sp[0];
     if (__any_sync(0xffffffffu, !(zmin >= Z_CUT))) {   // NaN -> evaluate
-        pr = 1.f;
-#pragma unroll
-        for (int u = 0; u < 2 * NP; u++) {
-            const float h = half_erfc(zv[u]);
-            float hm;
-            asm("{ .reg .pred p; setp.lt.f32 p, %1, %2; selp.f32 %0, %3, 0f00000000, p; }"
-                : "=f"(hm) : "f"(zv[u]), "f"(Z_CUT), "f"(h));
-            const float g = 1.f - hm;
-            pr *= sv[u] * g * g;
+        const u64 g0 = trunc_factor2(zp[0]);
+        prp = fmul2(fmul2(sp[0], g0), g0);
+        if (NP == 2) {
+            const u64 g1 = trunc_factor2(zp[1]);
+            prp = fmul2(prp, fmul2(fmul2(sp[1], g1), g1));
         }
-    } else {
-        pr = sv[0] * sv[1];
-        if (NP == 2) pr *= sv[2] * sv[3];
+    } else if (NP == 2) {
+        prp = fmul2(prp, sp[1]);
     }
-    return lg2_approx(pr);
+    float pa, pb;
+    unpack2(prp, pa, pb);
+    return lg2_approx(pa * pb);
 }
 
 template <int VARIANT>
