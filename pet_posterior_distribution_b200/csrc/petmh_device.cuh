@@ -371,7 +371,7 @@ __device__ __noinline__ float3 eval3(const int l16, const float d0, const float 
         // ---- likelihood of the block's 18 frames, one item per iteration (registers rotate) ----
         const float* crb = sCr + blk * RB;
 #pragma unroll 1
-        for (int it = 0; it < K; it++) {
+        for (int it = 0; it < K; it++) {   // (fully unrolling this loop was measured slower: code size)
             const float* yrow = sYcc + rowoff0 + blk * RSTRIDE;
             const float* crow = sCc + rowoff0 + blk * RSTRIDE;
             const u64 coefd = pack2(coef0, coef0), r1d = pack2(r10, r10);
