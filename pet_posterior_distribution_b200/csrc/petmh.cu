@@ -214,6 +214,13 @@ extern "C" int petmh_create(const petmh_cfg* cfg, petmh_t** out) {
     } while (0)
     CUC(cudaSetDevice(cfg->device));
     CUC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    {   // keep freed staging buffers cached in the stream-ordered pool (a trim at every sync cost ~0.6 s per set_data)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, cfg->device) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
     h->own_stream = true;
     CUC(cudaEventCreate(&h->ev0));
     CUC(cudaEventCreate(&h->ev1));
