@@ -141,6 +141,16 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float cos_approx(float x) {
+    float r;
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float rcp_approx(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -625,8 +635,9 @@ __global__ void __launch_bounds__(VARIANT == 0 ? 256 : 128, VARIANT == 0 ? 2 : 3
                     const uint4 x = philox4x32_10(
                         make_uint4((uint32_t)i, (uint32_t)(2 * sweep + b), (uint32_t)gid, (uint32_t)(gid >> 32)),
                         make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
-                    nrm = sqrtf(-2.f * __logf(u01(x.x))) * __cosf(6.283185307179586f * u01(x.y));
-                    logu[s] = __logf(u01(x.z));
+                    // Box-Muller (cos branch) with MUFU lg2 / sqrt / cos; ln u = lg2(u) * ln 2
+                    nrm = sqrt_approx(-1.3862943611198906f * lg2_approx(u01(x.x))) * cos_approx(6.283185307179586f * u01(x.y));
+                    logu[s] = 0.6931471805599453f * lg2_approx(u01(x.z));
                     key[s] = (x.w & 0xffffffc0u) | 0x80000000u | (uint32_t)i;   // > 0, unique, random order
                 }
                 q[s] = ST_F(sb + s);
