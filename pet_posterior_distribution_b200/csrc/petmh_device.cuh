@@ -488,10 +488,10 @@ __device__ __forceinline__ void load_tac_image(const SweepParams& p, int tac, un
     const double* cref = p.cref + (size_t)tac * NT;
     build_crs(p.ft, cref, sCrs, tid, nthr);
     for (int i = tid; i < 64; i += nthr) sCr[i] = i < NT ? (float)cref[i] : (i == K2P_SLOT ? p.k2p[tac] : 0.f);
-    if (tid < 48) sBad[tid] = 0;
     __syncthreads();
     build_M_packed(p.ft, sCrs, sM, tid, nthr);
     const float* y = p.y + (size_t)tac * NROI * NT;
+    int any_neg = 0;
     for (int i = tid; i < NROI * YS; i += nthr) {   // layout [roi][block][RSTRIDE], RB frames used
         const int r = i / YS, w = i - r * YS;
         const int blk = w / RSTRIDE, u = w - blk * RSTRIDE;
@@ -501,11 +501,15 @@ __device__ __forceinline__ void load_tac_image(const SweepParams& p, int tac, un
             c = p.cc[r * NT + j];
             const float yv = y[r * NT + j];
             yc = -(yv * c);   // stored negated: (s - y)/(sig sqrt2) = fma(s, cc, -y cc)
-            if (yv < 0.f) sBad[r] = 1;   // benign race: all writers store 1
+            if (yv < 0.f) any_neg = 1;
         }
         sCc[i] = c;
         sYcc[i] = yc;
     }
+    // an observation below the truncation bound makes the model log-probability -inf (mcmc.py:154):
+    // every Metropolis difference is then NaN and nothing ever moves, for ALL coordinates of the TAC
+    any_neg = __syncthreads_or(any_neg);
+    for (int i = tid; i < 48; i += nthr) sBad[i] = any_neg ? 1 : 0;   // (CTAs can be as small as 32 threads)
     __syncthreads();
 }
 

@@ -1,0 +1,97 @@
+"""Edge cases of the sampler on a real GPU: odd / single chain counts, thinning and capacity,
+degenerate data, resume, error behaviour of the C ABI."""
+import numpy as np
+import pytest
+
+from conftest import make_sampler
+
+pytestmark = pytest.mark.gpu
+
+
+def test_chain_streams_do_not_depend_on_chain_count(dataset, prior):
+    """Chain c of TAC 0 has Philox gid c whatever n_chains is: its draws are identical for
+    n_chains = 1, 3, 4 (different CTA shapes, idle half-warps) -> the thread mapping is invisible."""
+    runs = {}
+    for C in (1, 3, 4):
+        s = make_sampler(dataset, prior, n_chains=C, max_draws=30, seed=5, tacs=[0])
+        s.run(draws=30, tune=100)
+        runs[C] = s.chains()
+        assert runs[C][0].shape == (1, C, 30, 48) and np.isfinite(runs[C][0]).all()
+    assert np.array_equal(runs[1][0][0, 0], runs[4][0][0, 0]) and np.array_equal(runs[1][1][0, 0], runs[4][1][0, 0])
+    assert np.array_equal(runs[3][0][0, 2], runs[4][0][0, 2])
+    assert not np.array_equal(runs[4][0][0, 0], runs[4][0][0, 1])
+
+
+def test_thinning_and_capacity(dataset, prior):
+    full = make_sampler(dataset, prior, n_chains=2, max_draws=60, seed=9, tacs=[1])
+    full.run(draws=60, tune=100)
+    d_full = full.chains()[0]
+    thin = make_sampler(dataset, prior, n_chains=2, max_draws=20, seed=9, tacs=[1])
+    thin.run(draws=60, tune=100, thin=3)
+    assert thin.n_stored == 20
+    assert np.array_equal(thin.chains()[0], d_full[:, :, ::3])
+    cap = make_sampler(dataset, prior, n_chains=2, max_draws=10, seed=9, tacs=[1])
+    cap.run(draws=60, tune=100)                       # more draws than capacity: the first 10 are kept
+    assert cap.n_stored == 10 and np.array_equal(cap.chains()[0], d_full[:, :, :10])
+    none = make_sampler(dataset, prior, n_chains=2, max_draws=0, seed=9, tacs=[1])
+    none.run(draws=60, tune=100)
+    from pet_posterior_distribution_b200 import PetmhError
+    with pytest.raises(PetmhError):
+        none.chains()
+    assert np.isfinite(none.summary()[..., :2]).all()
+
+
+def test_negative_observation_freezes_the_chain(dataset, prior):
+    """y < 0 is outside the truncated support: the reference's log-probability is -inf, every
+    delta_logp is NaN and metrop_select rejects everything -- the chain stays at the prior mean."""
+    from pet_posterior_distribution_b200 import MHSampler
+    s = MHSampler(n_chains=2, max_tacs=2, max_draws=5, seed=1)
+    s.set_frames(dataset["time_vector"], dataset["dt"])
+    s.set_prior(prior["mu_DVR"], prior["Cov_DVR"], prior["mu_R1"], prior["Cov_R1"])
+    y = dataset["tac_noisy_sampled"][:2] / dataset["dt"][None, None, :]
+    y[0, 7, 20] = -0.5
+    s.set_data(y, dataset["vartacref"][:2], dataset["vark2p"][:2], dataset["sigma_noise"])
+    s.run(draws=5, tune=100)
+    dvr, r1 = s.chains()
+    assert (dvr[0] == prior["mu_DVR"].astype(np.float32)).all() and (r1[0] == prior["mu_R1"].astype(np.float32)).all()
+    assert (dvr[1] != prior["mu_DVR"].astype(np.float32)).any()
+    ll, _ = s.loglik(0, prior["mu_DVR"], prior["mu_R1"])
+    assert np.isneginf(ll).all()
+
+
+def test_state_roundtrip_resume(dataset, prior):
+    a = make_sampler(dataset, prior, n_chains=4, max_draws=0, seed=3, tacs=[0, 1])
+    a.run(draws=0, tune=300)
+    q, sc = a.state()
+    assert q.shape == (2, 4, 96) and (sc > 0).all() and (sc < 1).all()
+    b = make_sampler(dataset, prior, n_chains=4, max_draws=0, seed=3, tacs=[0, 1])
+    b.set_state(q, sc, sweep=300)
+    b.plan(draws=50, tune=300)
+    a.plan(draws=50, tune=300)
+    a.advance(50)
+    b.advance(50)
+    qa, sa = a.state()
+    qb, sb = b.state()
+    assert np.array_equal(qa, qb) and np.array_equal(sa, sb)       # warm start == continued run
+    assert np.array_equal(sa, sc)                                   # scaling frozen after tuning
+
+
+def test_error_behaviour(dataset, prior):
+    from pet_posterior_distribution_b200 import MHSampler, PetmhError
+    s = MHSampler(n_chains=2, max_tacs=1)
+    with pytest.raises(PetmhError) as e:
+        s.run(10, 10)
+    assert e.value.code == -1
+    s.set_frames(dataset["time_vector"], dataset["dt"])
+    s.set_prior(prior["mu_DVR"], prior["Cov_DVR"], prior["mu_R1"], prior["Cov_R1"])
+    y = dataset["tac_noisy_sampled"][:2] / dataset["dt"][None, None, :]
+    with pytest.raises(PetmhError):                                 # more TACs than capacity
+        s.set_data(y, dataset["vartacref"][:2], dataset["vark2p"][:2], dataset["sigma_noise"])
+    with pytest.raises(PetmhError):                                 # sigma_noise never given
+        s.set_data(y[:1], dataset["vartacref"][:1], dataset["vark2p"][:1], None)
+    with pytest.raises(PetmhError):                                 # not positive definite
+        s.set_prior(prior["mu_DVR"], -np.eye(48), prior["mu_R1"], prior["Cov_R1"])
+    with pytest.raises(PetmhError):
+        MHSampler(n_chains=0)
+    with pytest.raises(ValueError):
+        s.set_frames(np.zeros(10), np.zeros(10))
