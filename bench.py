@@ -239,6 +239,26 @@ def run_b200(args):
         except Exception as e:      # pragma: no cover
             cfg2 = {"error": repr(e)}
 
+    # ---- chain storage leg (north star: achieved HBM GB/s of the thinned-chain writes), rank 0 -------------
+    store = None
+    if rank == 0:
+        try:
+            S3, D3 = 8192, 64
+            with MHSampler(n_chains=C, max_tacs=S3, max_draws=D3, seed=5, device=local) as s3:
+                s3.set_frames(t, dtv)
+                s3.set_prior(prior["mu_DVR"], prior["Cov_DVR"], prior["mu_R1"], prior["Cov_R1"])
+                s3.set_data(yb[np.arange(S3) % nb], cb[np.arange(S3) % nb], k_pin.numpy()[:S3], sig)
+                s3.set_state(q0[np.arange(S3) % nb], sc0[np.arange(S3) % nb], sweep=TUNE)
+                s3.plan(draws=D3, tune=TUNE, thin=1)
+                s3.advance(D3)
+                ms3, _ = s3.last_kernel_ms()
+            nbytes = S3 * C * D3 * 96 * 4
+            store = {"workload": "%d TACs x %d chains, %d draws stored (thin 1)" % (S3, C, D3), "bytes_per_stored_sweep_per_chain": 384,
+                     "bytes_written": nbytes, "kernel_ms": ms3, "achieved_GBps": nbytes / (ms3 * 1e-3) / 1e9,
+                     "chain_steps_per_s_with_storage": S3 * C * 96 * D3 / (ms3 * 1e-3)}
+        except Exception as e:      # pragma: no cover
+            store = {"error": repr(e)}
+
     tt = torch.tensor([dev_ms * 1e-3, wall, e2e_wall], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -285,7 +305,7 @@ def run_b200(args):
                        "tacs_per_gpu": S, "chains_per_tac": C, "sweeps_per_step": SW, "chain_steps_per_step": steps_per_step,
                        "l2_policy": "per-step working set (inputs+state %.1f GB) >> 126 MB L2" % ((S * 10588 + S * C * 3500) / 1e9),
                        "sec_per_48roi_posterior_60000_sweeps_amortised": 60000 * 96 * C / (value / world) ,
-                       "summary_finite": ok, "sec_per_48roi_posterior": cfg2},
+                       "summary_finite": ok, "sec_per_48roi_posterior": cfg2, "chain_storage": store},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "chain-steps/s", "h2d_bytes_per_step": int(S * (48 * 54 + 54 + 1) * 4) * world,
                     "d2h_bytes_per_step": int(S * 96 * 8 * 4) * world,
@@ -294,7 +314,7 @@ def run_b200(args):
             "roofline": {"bound": "fp32", "achieved": ach, "peak": peak_fp32, "unit": "TFLOP/s", "frac": ach / peak_fp32,
                          # dram__bytes_read+write of one mh_sweep_kernel launch at the default workload
                          # (131072 TACs x 16 chains, 50 sweeps), ncu capture profiles/r01_ncu_sweep_dram_bench.csv
-                         "traffic": 18139866624 if (S == 131072 and SW == 50) else None,
+                         "traffic": 18139866624 if (S == 131072 and SW == 50) else None,   # (measured at 50 sweeps per launch)
                          "note": "dominant kernel mh_sweep_kernel (%.1f %% of the step by CUDA events on its stream); achieved = "
                                  "3980 algorithmic FP32 flop/chain-step x per-GPU kernel rate; peak = 148 SM x 128 lanes x 2 x SM clock "
                                  "under load (nominal formula: MEASURED_PEAKS.json has no FP32 figure)" % (100 * dev_s / wall_s),
@@ -315,7 +335,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tacs-per-gpu", type=int, default=131072)
     ap.add_argument("--base-tacs", type=int, default=1024)
-    ap.add_argument("--sweeps", type=int, default=50)
+    ap.add_argument("--sweeps", type=int, default=100)
     ap.add_argument("--tune", type=int, default=1500)
     ap.add_argument("--cpu-sweeps", type=int, default=40)
     ap.add_argument("--ref-sweeps", type=int, default=8)
