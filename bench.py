@@ -153,32 +153,27 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     S, C, SW = args.tacs_per_gpu, N_CHAINS, args.sweeps
 
-    # ---- synthetic inputs: n_base unique TACs from the restated generator, tiled to S -------
+    # ---- synthetic inputs: S unique training-style TACs per rank, generated on the GPU (K4) ------------------
     prior = gen.load_prior()
-    nb = min(args.base_tacs, S)
-    ds = gen.generate(prior, nb, 0.1, test_style=False, seed=1234 + rank, device=local)
-    t, dtv = ds["time_vector"], ds["dt"]
-    yb = (np.asarray(ds["tac_noisy_sampled"]) / dtv[None, None, :]).astype(np.float32)
-    cb = np.asarray(ds["vartacref"], np.float32)
-    idx = np.arange(S) % nb
-    y_pin = torch.empty((S, 48, 54), dtype=torch.float32, pin_memory=True)
-    c_pin = torch.empty((S, 54), dtype=torch.float32, pin_memory=True)
-    k_pin = torch.full((S,), float(prior["mu_k2p"]), dtype=torch.float32).pin_memory()
-    y_pin.numpy()[:] = yb[idx]
-    c_pin.numpy()[:] = cb[idx]
-    out_pin = torch.empty((S, 96, 8), dtype=torch.float32, pin_memory=True)
-    sig = np.ascontiguousarray(ds["sigma_noise"], np.float32)
-
+    t, dtv = gen.frame_grid()
+    sig64 = gen.noise_table(np.random.default_rng(1234), 0.1, t, dtv)     # one sigma_noise table for the data set
+    sig = np.ascontiguousarray(sig64, np.float32)
     s = MHSampler(n_chains=C, max_tacs=S, max_draws=0, seed=2026, device=local, tac_gid0=rank * S)
     s.set_frames(t, dtv)
     s.set_prior(prior["mu_DVR"], prior["Cov_DVR"], prior["mu_R1"], prior["Cov_R1"])
-    s.set_data(yb, cb, k_pin.numpy()[:nb], sig)          # base set only: tune it
+    s.synth(S, 4321, prior["mu_tac_ref"], prior["Cov_tac_ref"], float(prior["mu_k2p"]), sig64)
+    g = s.synth_get()                                       # host copies (pinned) for the end-to-end leg
+    y_pin = torch.empty((S, 48, 54), dtype=torch.float32, pin_memory=True)
+    c_pin = torch.empty((S, 54), dtype=torch.float32, pin_memory=True)
+    k_pin = torch.full((S,), float(prior["mu_k2p"]), dtype=torch.float32).pin_memory()
+    y_pin.numpy()[:] = g["y"]
+    c_pin.numpy()[:] = g["tac_ref"]
+    out_pin = torch.empty((S, 96, 8), dtype=torch.float32, pin_memory=True)
+    yb, cb, nb = g["y"], g["tac_ref"].astype(np.float32), S
+    del g
     TUNE = args.tune
-    s.run(draws=0, tune=TUNE)
-    q0, sc0 = s.state()                                    # (nb, C, 96) tuned positions / scalings
-    # full batch, warm-started from the tuned base chains (Philox streams differ per TAC gid)
-    s.set_data_ptr(S, y_pin.data_ptr(), c_pin.data_ptr(), k_pin.data_ptr(), None)
-    s.set_state(q0[idx], sc0[idx], sweep=TUNE)
+    s.run(draws=0, tune=TUNE)                              # every chain tuned on its own TAC (untimed set-up)
+    q0, sc0 = s.state()
     s.plan(draws=10 ** 8, tune=TUNE, thin=1)
 
     def barrier():
@@ -298,7 +293,7 @@ def run_b200(args):
             "metric": "MH chain-steps/sec (SRTM2 lik)", "value": value, "unit": "chain-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall_s / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic: %d unique SRTM2 TACs per rank from the restated sample_sim_data.py priors (sigma 0.1), tiled to %d" % (nb, S),
+            "data": "synthetic: %d unique SRTM2 TACs per rank generated on the GPU (K4 petmh_synth: restated sample_sim_data.py training-style priors, sigma 0.1)" % S,
             "config": {"workload": "BASELINE configs[4] throughput scaling, TAC-sharded: %d TACs/GPU x %d chains x 48 ROIs "
                                    "(1M TACs at 8 GPUs); step = %d sweeps (x96 chain-steps) of every chain, draw phase after "
                                    "%d tuning sweeps" % (S, C, SW, TUNE),
@@ -334,9 +329,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tacs-per-gpu", type=int, default=131072)
-    ap.add_argument("--base-tacs", type=int, default=1024)
     ap.add_argument("--sweeps", type=int, default=100)
-    ap.add_argument("--tune", type=int, default=1500)
+    ap.add_argument("--tune", type=int, default=1000)
     ap.add_argument("--cpu-sweeps", type=int, default=40)
     ap.add_argument("--ref-sweeps", type=int, default=8)
     ap.add_argument("--ref-mode", default="faithful", choices=["faithful", "lean"])

@@ -74,6 +74,17 @@ int petmh_set_data(petmh_t* h, int n_tac, const double* y, const double* tac_ref
 int petmh_set_data_f32(petmh_t* h, int n_tac, const float* y, const float* tac_ref,
                        const float* k2p, const float* sigma_noise);
 
+/* ---- synthetic inputs on the GPU (K4; replaces sample_sim_data.py:141-215 for the training-style set) ----
+ * Draw, per TAC, DVR / R1 from the handle's priors and the reference TAC from N(mu_tacref, cov_tacref)
+ * with positivity rejection (helper_func.py:153-162), forward-simulate, redraw while any clean TAC value is
+ * negative (sample_sim_data.py:171-188), add the truncated signal-dependent noise (:205-215) and leave
+ * y (= noisy concentration), tac_ref and k2p in the handle as if petmh_set_data had been called. */
+int petmh_synth(petmh_t* h, int n_tac, uint64_t seed, const double* mu_tacref54, const double* cov_tacref54x54,
+                double k2p, const double* sigma_noise48x54);
+/* what petmh_synth generated (any pointer may be NULL): dvr_r1[n][96] f32, tac_ref[n][54] f64,
+ * tac_clean[n][48][54] f32 and y[n][48][54] f32 in concentration units, attempts[n]. */
+int petmh_synth_get(petmh_t* h, float* dvr_r1, double* tac_ref, float* tac_clean, float* y, int* attempts);
+
 /* ---- parity hooks ------------------------------------------------------------------ */
 /* replaces CreateTAC_SRTM2.perform (mcmc.py:38-39) == SRTM2.create_activity_curve(...).T
  * (kinetic_model.py:142-158): out[48][54], unclamped. */

@@ -42,6 +42,8 @@ def _load():
         "petmh_set_prior": (C.c_int, [H, dp, dp, dp, dp]),
         "petmh_set_data": (C.c_int, [H, C.c_int, dp, dp, dp, dp]),
         "petmh_set_data_f32": (C.c_int, [H, C.c_int, fp, fp, fp, fp]),
+        "petmh_synth": (C.c_int, [H, C.c_int, C.c_uint64, dp, dp, C.c_double, dp]),
+        "petmh_synth_get": (C.c_int, [H, fp, dp, fp, fp, C.POINTER(C.c_int)]),
         "petmh_forward": (C.c_int, [H, C.c_int, dp, dp, dp]),
         "petmh_loglik": (C.c_int, [H, C.c_int, dp, dp, dp, dp]),
         "petmh_get_operator": (C.c_int, [H, C.c_int, dp]),

@@ -12,6 +12,7 @@
 #include "petmh_device.cuh"
 #include "petmh_diag.cuh"
 #include "petmh_rankdiag.cuh"
+#include "petmh_synth.cuh"
 
 using namespace petmh;
 
@@ -43,6 +44,11 @@ struct petmh_handle {
     float *d_q = nullptr, *d_scale = nullptr, *d_mom = nullptr, *d_draws = nullptr, *d_mom_first = nullptr;
     float4* d_momw = nullptr;
     float* d_summary = nullptr;   // [max_tacs][96][8], allocated on first petmh_get_summary
+    // K4 generator
+    double cov[2][48 * 48]{};
+    double* d_synth_f64 = nullptr;   // factors + means
+    float *d_synth_truth = nullptr, *d_synth_clean = nullptr;
+    int* d_synth_attempts = nullptr;
     uint8_t* d_cnt = nullptr;
     uint32_t* d_nacc = nullptr;
     // schedule
@@ -245,6 +251,7 @@ extern "C" int petmh_create(const petmh_cfg* cfg, petmh_t** out) {
     CUC(cudaFuncSetAttribute(mh_sweep_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(256)));
     CUC(cudaFuncSetAttribute(mh_sweep_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(128)));
     CUC(cudaFuncSetAttribute(mh_sweep_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(256)));
+    CUC(cudaFuncSetAttribute(synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_STATE + 32 * SLOTS * NT * 4));
     CUC(cudaFuncSetAttribute(forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_STATE + 32 * SLOTS * NT * 4));
 #undef CUC
     *out = h;
@@ -255,7 +262,8 @@ extern "C" void petmh_destroy(petmh_t* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     void* bufs[] = {h->d_ft, h->d_P, h->d_mu, h->d_cc, h->d_y, h->d_cref, h->d_k2p, h->d_q, h->d_scale,
-                    h->d_cnt, h->d_nacc, h->d_mom, h->d_draws, h->d_scratch, h->d_scratch64, h->d_momw, h->d_mom_first, h->d_summary};
+                    h->d_cnt, h->d_nacc, h->d_mom, h->d_draws, h->d_scratch, h->d_scratch64, h->d_momw, h->d_mom_first, h->d_summary, h->d_synth_f64, h->d_synth_truth,
+                    h->d_synth_clean, h->d_synth_attempts};
     for (void* b : bufs) if (b) cudaFree(b);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -314,6 +322,7 @@ extern "C" int petmh_set_prior(petmh_t* h, const double* mu_dvr, const double* c
     const double* mus[2] = {mu_dvr, mu_r1};
     for (int b = 0; b < 2; b++) {
         memcpy(h->mu[b], mus[b], 48 * sizeof(double));
+        memcpy(h->cov[b], covs[b], 48 * 48 * sizeof(double));
         if (!spd_inverse(covs[b], 48, h->P.data() + b * 48 * 48, &h->logdet[b]))
             return fail(h, PETMH_EINVAL, "prior covariance %d is not positive definite", b);
     }
@@ -731,6 +740,107 @@ extern "C" int petmh_get_summary(petmh_t* h, float* out) {
     int rc = petmh_summary_device(h, h->d_summary, nullptr);
     if (rc) return rc;
     CU(cudaMemcpyAsync(out, h->d_summary, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return PETMH_OK;
+}
+
+// ---- K4: synthetic data on the GPU ---------------------------------------------------------
+// pivoted Cholesky of a symmetric positive SEMI-definite matrix: cov ~= A A^T, A is n x rank
+// (numpy.random.multivariate_normal tolerates the rank-deficient Cov_tac_ref through an SVD; any
+// factor with A A^T = cov gives the same distribution).  Returns A transposed (AT[k][j]).
+static int psd_factor_T(const double* cov, int n, std::vector<double>& AT) {
+    std::vector<double> a(cov, cov + n * n), L(n * n, 0.0);
+    std::vector<int> piv(n);
+    for (int i = 0; i < n; i++) piv[i] = i;
+    double dmax0 = 0.0;
+    for (int i = 0; i < n; i++) dmax0 = std::max(dmax0, a[i * n + i]);
+    int rank = 0;
+    for (int k = 0; k < n; k++) {
+        int best = k;
+        for (int i = k + 1; i < n; i++) if (a[piv[i] * n + piv[i]] > a[piv[best] * n + piv[best]]) best = i;
+        std::swap(piv[k], piv[best]);
+        const int pk = piv[k];
+        const double d = a[pk * n + pk];
+        if (!(d > 1e-13 * dmax0)) break;
+        const double l = std::sqrt(d);
+        L[pk * n + k] = l;
+        for (int i = k + 1; i < n; i++) {
+            const int pi = piv[i];
+            L[pi * n + k] = a[pi * n + pk] / l;
+        }
+        for (int i = k + 1; i < n; i++)
+            for (int j = k + 1; j < n; j++) {
+                const int pi = piv[i], pj = piv[j];
+                a[pi * n + pj] -= L[pi * n + k] * L[pj * n + k];
+            }
+        rank++;
+    }
+    AT.assign((size_t)n * n, 0.0);
+    for (int k = 0; k < rank; k++)
+        for (int j = 0; j < n; j++) AT[(size_t)k * n + j] = L[j * n + k];
+    return rank;
+}
+
+extern "C" int petmh_synth(petmh_t* h, int n_tac, uint64_t seed, const double* mu_tacref54, const double* cov_tacref54x54,
+                           double k2p, const double* sigma_noise48x54) {
+    if (!h || !mu_tacref54 || !cov_tacref54x54 || !sigma_noise48x54) return fail(h, PETMH_EINVAL, "null argument");
+    if (!h->have_frames || !h->have_prior) return fail(h, PETMH_EINVAL, "petmh_set_frames / petmh_set_prior not called");
+    if (n_tac < 1 || n_tac > h->cfg.max_tacs) return fail(h, PETMH_EINVAL, "n_tac %d outside [1, max_tacs=%d]", n_tac, h->cfg.max_tacs);
+    CU(cudaSetDevice(h->cfg.device));
+    int rc = upload_noise(h, sigma_noise48x54);
+    if (rc) return rc;
+    // factors and means: [AT_dvr 48x48 | AT_r1 48x48 | AT_ref 54x54 | mu_dvr 48 | mu_r1 48 | mu_ref 54]
+    std::vector<double> buf, at;
+    SynthParams sp{};
+    const double* covs[3] = {h->cov[0], h->cov[1], cov_tacref54x54};
+    const double* mus[3] = {h->mu[0], h->mu[1], mu_tacref54};
+    const int dims[3] = {48, 48, 54};
+    size_t off[3], moff[3];
+    for (int v = 0; v < 3; v++) {
+        sp.dim[v] = dims[v];
+        sp.rank[v] = psd_factor_T(covs[v], dims[v], at);
+        if (sp.rank[v] < 1) return fail(h, PETMH_EINVAL, "covariance %d has no positive direction", v);
+        off[v] = buf.size();
+        buf.insert(buf.end(), at.begin(), at.end());
+    }
+    for (int v = 0; v < 3; v++) { moff[v] = buf.size(); buf.insert(buf.end(), mus[v], mus[v] + dims[v]); }
+    std::vector<float> sig(48 * NT);
+    for (int i = 0; i < 48 * NT; i++) sig[i] = (float)sigma_noise48x54[i];
+    if (!h->d_synth_f64) CU(cudaMalloc(&h->d_synth_f64, (48 * 48 * 2 + 54 * 54 + 48 * 2 + 54) * sizeof(double) + 48 * NT * sizeof(float)));
+    const size_t S = h->cfg.max_tacs;
+    if (!h->d_synth_truth) CU(cudaMalloc(&h->d_synth_truth, S * 96 * sizeof(float)));
+    if (!h->d_synth_clean) CU(cudaMalloc(&h->d_synth_clean, S * 48 * NT * sizeof(float)));
+    if (!h->d_synth_attempts) CU(cudaMalloc(&h->d_synth_attempts, S * sizeof(int)));
+    CU(cudaMemcpyAsync(h->d_synth_f64, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    float* d_sig = reinterpret_cast<float*>(h->d_synth_f64 + buf.size());
+    CU(cudaMemcpyAsync(d_sig, sig.data(), sig.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    for (int v = 0; v < 3; v++) { sp.AT[v] = h->d_synth_f64 + off[v]; sp.mu3[v] = h->d_synth_f64 + moff[v]; }
+    sp.sigma = d_sig;
+    sp.k2p = (float)k2p;
+    sp.seed = seed;
+    sp.tac_gid0 = h->cfg.tac_gid0;
+    sp.n_tac = n_tac;
+    sp.y = h->d_y; sp.cref = h->d_cref; sp.k2p_out = h->d_k2p;
+    sp.truth = h->d_synth_truth; sp.clean = h->d_synth_clean; sp.attempts = h->d_synth_attempts;
+    h->n_tac = n_tac;
+    SweepParams p = base_params(h);
+    synth_kernel<<<n_tac, 64, SM_STATE + 32 * SLOTS * NT * 4, h->stream>>>(p, sp);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    h->have_data = true;
+    return PETMH_OK;
+}
+
+extern "C" int petmh_synth_get(petmh_t* h, float* dvr_r1 /*[n][96]*/, double* tac_ref /*[n][54]*/, float* tac_clean /*[n][48][54]*/,
+                               float* y /*[n][48][54]*/, int* attempts /*[n]*/) {
+    if (!h || !h->d_synth_truth) return fail(h, PETMH_EINVAL, "petmh_synth not called");
+    CU(cudaSetDevice(h->cfg.device));
+    const size_t n = h->n_tac;
+    if (dvr_r1) CU(cudaMemcpyAsync(dvr_r1, h->d_synth_truth, n * 96 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (tac_ref) CU(cudaMemcpyAsync(tac_ref, h->d_cref, n * NT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (tac_clean) CU(cudaMemcpyAsync(tac_clean, h->d_synth_clean, n * 48 * NT * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (y) CU(cudaMemcpyAsync(y, h->d_y, n * 48 * NT * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (attempts) CU(cudaMemcpyAsync(attempts, h->d_synth_attempts, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return PETMH_OK;
 }

@@ -46,7 +46,39 @@ def _trunc_normal(rng, mean, std, low):
     return spst.truncnorm.rvs(a, np.inf, loc=mean, scale=std, random_state=rng)
 
 
+def noise_table(rng, mean_sigma_noise, t, dt, nroi=48):
+    """sigma_noise (48,54) of sample_sim_data.py:193-201: per-ROI level ~ TruncNormal(mean, 0.3 mean, low=0),
+    scaled by 1/sqrt(dt * exp(-lambda t)), lambda = ln2 / 109.8 min."""
+    lam = np.log(2) / MK_HALF_T
+    sigma_roi = _trunc_normal(rng, np.full(nroi, mean_sigma_noise), 0.3 * mean_sigma_noise, 0.0)
+    return sigma_roi[:, None] / np.sqrt(dt[None, :] * np.exp(-lam * t))
+
+
+def generate_gpu(prior, n, mean_sigma_noise=0.1, seed=0, device=0, sampler=None):
+    """Training-style set generated entirely on the B200 (K4, petmh_synth): returns the reference's
+    pickle schema.  With `sampler` given, the batch stays bound to it as its data (no host round trip)."""
+    rng = np.random.default_rng(seed)
+    t, dt = frame_grid()
+    sigma_noise = noise_table(rng, mean_sigma_noise, t, dt)
+    own = sampler is None
+    s = sampler or MHSampler(n_chains=1, max_tacs=n, device=device)
+    if own:
+        s.set_frames(t, dt)
+        s.set_prior(prior["mu_DVR"], prior["Cov_DVR"], prior["mu_R1"], prior["Cov_R1"])
+    s.synth(n, seed, prior["mu_tac_ref"], prior["Cov_tac_ref"], float(prior["mu_k2p"]), sigma_noise)
+    g = s.synth_get()
+    if own:
+        s.close()
+    return {"varDVR": list(g["DVR"].astype(np.float64)), "varR1": list(g["R1"].astype(np.float64)),
+            "vark2p": [prior["mu_k2p"] for _ in range(n)], "vartacref": list(g["tac_ref"]),
+            "tac_sampled": list(g["tac_clean"].astype(np.float64) * dt[None, None, :]),
+            "tac_noisy_sampled": list(g["y"].astype(np.float64) * dt[None, None, :]),
+            "mu_noise": np.zeros_like(sigma_noise), "sigma_noise": sigma_noise, "mean_sigma_noise": mean_sigma_noise,
+            "flag_mahalanobis": False, "target_ROI_names": prior.get("ROI_names"), "time_vector": t, "dt": dt}
+
+
 def generate(prior, n, mean_sigma_noise=0.1, test_style=False, seed=0, device=0, alpha_=0.8):
+    """Host draws + GPU forward model; supports the test-style Mahalanobis rule (sample_sim_data.py:128-133)."""
     rng = np.random.default_rng(seed)
     t, dt = frame_grid()
     nroi = prior["mu_DVR"].size
@@ -68,9 +100,7 @@ def generate(prior, n, mean_sigma_noise=0.1, test_style=False, seed=0, device=0,
             DVR[bad], R1[bad], cref[bad] = draw("DVR", bad.size), draw("R1", bad.size), draw("tac_ref", bad.size)
         todo = bad
     fwd.close()
-    lam = np.log(2) / MK_HALF_T                        # :193
-    sigma_roi = _trunc_normal(rng, np.full(nroi, mean_sigma_noise), 0.3 * mean_sigma_noise, 0.0)
-    sigma_noise = sigma_roi[:, None] / np.sqrt(dt[None, :] * np.exp(-lam * t))
+    sigma_noise = noise_table(rng, mean_sigma_noise, t, dt, nroi)       # :193-201
     noisy = tac + np.sqrt(tac) * _trunc_normal(rng, np.zeros_like(tac), np.broadcast_to(sigma_noise, tac.shape),
                                                -np.sqrt(tac))                                  # :205-215
     return {"varDVR": list(DVR), "varR1": list(R1), "vark2p": [prior["mu_k2p"] for _ in range(n)],
@@ -96,7 +126,9 @@ def load_prior(path=None):
 def main():
     """Write sim_data/nROI48/<ts>_{train,test}/data_*.pik + args_*.txt (sample_sim_data.py:218-240)."""
     prior = load_prior()
-    ds = generate(prior, n_samples, mean_sigma_noise_save, flag_testing_data, seed=int(datetime.now().timestamp()), alpha_=alpha)
+    sd = int(datetime.now().timestamp())
+    ds = generate(prior, n_samples, mean_sigma_noise_save, True, seed=sd, alpha_=alpha) if flag_testing_data else \
+        generate_gpu(prior, n_samples, mean_sigma_noise_save, seed=sd)
     str_test = "_test" if flag_testing_data else "_train"
     str_noise = "_s{:.1e}".format(mean_sigma_noise_save)
     d = os.path.join("./sim_data", "nROI{}".format(n_ROI), datetime.now().strftime("%y-%m-%d_%H-%M-%S") + str_test)

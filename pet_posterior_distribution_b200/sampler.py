@@ -106,6 +106,27 @@ class MHSampler:
         """Summary (S,96,8) f32 into a raw HOST pointer (e.g. pinned memory)."""
         self._ck(_lib.lib.petmh_get_summary(self._h, C.cast(C.c_void_p(int(out_ptr)), C.POINTER(C.c_float))))
 
+    def synth(self, n_tac, seed, mu_tac_ref, Cov_tac_ref, k2p, sigma_noise):
+        """K4: generate n_tac training-style synthetic TACs on the GPU and bind them as this sampler's data."""
+        mu = np.ascontiguousarray(mu_tac_ref, np.float64)
+        cov = np.ascontiguousarray(Cov_tac_ref, np.float64)
+        sn = np.ascontiguousarray(sigma_noise, np.float64)
+        if mu.shape != (N_FRAMES,) or cov.shape != (N_FRAMES, N_FRAMES) or sn.shape != (N_ROI, N_FRAMES):
+            raise ValueError("mu_tac_ref (54,), Cov_tac_ref (54,54), sigma_noise (48,54) expected")
+        self._ck(_lib.lib.petmh_synth(self._h, int(n_tac), int(seed), _d(mu), _d(cov), float(k2p), _d(sn)))
+        self.n_tac = int(n_tac)
+
+    def synth_get(self):
+        """dict(DVR (n,48), R1 (n,48), tac_ref (n,54), tac_clean (n,48,54), y (n,48,54), attempts (n,))."""
+        n = self.n_tac
+        dr = np.empty((n, N_COORD), np.float32)
+        cr = np.empty((n, N_FRAMES), np.float64)
+        cl = np.empty((n, N_ROI, N_FRAMES), np.float32)
+        y = np.empty((n, N_ROI, N_FRAMES), np.float32)
+        at = np.empty(n, np.int32)
+        self._ck(_lib.lib.petmh_synth_get(self._h, _f(dr), _d(cr), _f(cl), _f(y), at.ctypes.data_as(C.POINTER(C.c_int))))
+        return dict(DVR=dr[:, :N_ROI].copy(), R1=dr[:, N_ROI:].copy(), tac_ref=cr, tac_clean=cl, y=y, attempts=at)
+
     # -- parity hooks ---------------------------------------------------------------------
     def forward(self, tac, DVR, R1):
         """(48,54) model TAC, == SRTM2.create_activity_curve(DVR,R1,k2p).T (mcmc.py:38-39)."""
