@@ -89,6 +89,9 @@ int petmh_synth_get(petmh_t* h, float* dvr_r1, double* tac_ref, float* tac_clean
 /* replaces CreateTAC_SRTM2.perform (mcmc.py:38-39) == SRTM2.create_activity_curve(...).T
  * (kinetic_model.py:142-158): out[48][54], unclamped. */
 int petmh_forward(petmh_t* h, int tac, const double* dvr48, const double* r1_48, double* out48x54);
+/* replaces SRTM.forward_model(DVR, k2, R1, tac_ref).T (kinetic_model.py:69-84; k2 free per ROI): out[48][54] */
+int petmh_forward_srtm(petmh_t* h, int tac, const double* dvr48, const double* k2_48, const double* r1_48,
+                       double* out48x54);
 /* replaces the model log-probability pieces (mcmc.py:148-155): ll48[i] = sum_t log
  * TruncatedNormal(y_it | mu=sn_it, sigma=sqrt(sn_it) sigma_noise_it, lower=0) including the
  * state-independent constants; logprior2 = {log MvNormal(DVR), log MvNormal(R1)}. */

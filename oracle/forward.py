@@ -104,3 +104,13 @@ def srtm2_tac_M(t, c_r, M, DVR, R1, k2p):
     k2a = k2 / DVR
     e = np.exp(-k2a[None, :] * np.asarray(t)[:, None])
     return R1[None, :] * np.asarray(c_r)[:, None] + (k2 - R1 * k2a)[None, :] * (M @ e)
+
+
+def srtm_tac(t, c_r, DVR, k2, R1):
+    """SRTM.forward_model (kinetic_model.py:69-84): k2 is a free parameter per ROI. Returns (T, R)."""
+    DVR = np.atleast_1d(np.asarray(DVR, np.float64))
+    R1 = np.atleast_1d(np.asarray(R1, np.float64))
+    k2 = np.atleast_1d(np.asarray(k2, np.float64))
+    k2a = k2 / DVR
+    c_exp = np.exp(-k2a[None, :] * np.asarray(t)[:, None])
+    return R1[None, :] * np.asarray(c_r)[:, None] + (k2 - R1 * k2a)[None, :] * continuous_convolution(t, c_r, c_exp)

@@ -45,6 +45,7 @@ def _load():
         "petmh_synth": (C.c_int, [H, C.c_int, C.c_uint64, dp, dp, C.c_double, dp]),
         "petmh_synth_get": (C.c_int, [H, fp, dp, fp, fp, C.POINTER(C.c_int)]),
         "petmh_forward": (C.c_int, [H, C.c_int, dp, dp, dp]),
+        "petmh_forward_srtm": (C.c_int, [H, C.c_int, dp, dp, dp, dp]),
         "petmh_loglik": (C.c_int, [H, C.c_int, dp, dp, dp, dp]),
         "petmh_get_operator": (C.c_int, [H, C.c_int, dp]),
         "petmh_philox_raw": (C.c_int, [H, C.c_uint64, C.c_uint32, C.c_uint32, u32p]),

@@ -491,6 +491,27 @@ extern "C" int petmh_loglik(petmh_t* h, int tac, const double* dvr48, const doub
     return PETMH_OK;
 }
 
+extern "C" int petmh_forward_srtm(petmh_t* h, int tac, const double* dvr48, const double* k2_48, const double* r1_48,
+                                  double* out48x54) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!dvr48 || !k2_48 || !r1_48 || !out48x54) return fail(h, PETMH_EINVAL, "null argument");
+    if (tac < 0 || tac >= h->n_tac) return fail(h, PETMH_EINVAL, "tac index out of range");
+    CU(cudaSetDevice(h->cfg.device));
+    float in[144];
+    for (int i = 0; i < 48; i++) { in[i] = (float)dvr48[i]; in[48 + i] = (float)k2_48[i]; in[96 + i] = (float)r1_48[i]; }
+    float* d_in = h->d_scratch + 48 * NT + 64;
+    CU(cudaMemcpyAsync(d_in, in, sizeof in, cudaMemcpyHostToDevice, h->stream));
+    SweepParams p = base_params(h);
+    forward_srtm_kernel<<<1, 256, 0, h->stream>>>(p, tac, d_in, d_in + 48, d_in + 96, h->d_scratch);
+    CU(cudaGetLastError());
+    std::vector<float> t(48 * NT);
+    CU(cudaMemcpyAsync(t.data(), h->d_scratch, 48 * NT * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < 48 * NT; i++) out48x54[i] = t[i];
+    return PETMH_OK;
+}
+
 extern "C" int petmh_get_operator(petmh_t* h, int tac, double* m) {
     int rc = check_ready(h);
     if (rc) return rc;

@@ -829,6 +829,31 @@ __global__ void forward_kernel(const SweepParams p, int tac, const float* dvr, c
     }
 }
 
+// SRTM with k2 free (kinetic_model.py:69-84), the other model of the reference's kinetic_model.py
+// (SURVEY.md 8 f3): TAC = R1 c_r + (k2 - R1 k2a) M exp(-k2a t), k2a = k2 / DVR.  Straightforward fp32
+// evaluation with the dense operator in shared memory (not a hot path: mcmc.py never calls SRTM).
+__global__ void forward_srtm_kernel(const SweepParams p, int tac, const float* dvr, const float* k2, const float* r1,
+                                    float* tac_out /*[48][54]*/) {
+    __shared__ double crs[NGRID];
+    __shared__ float Md[NT * NCOL];
+    __shared__ float cr[NT];
+    const double* cref = p.cref + (size_t)tac * NT;
+    build_crs(p.ft, cref, crs, threadIdx.x, blockDim.x);
+    for (int i = threadIdx.x; i < NT; i += blockDim.x) cr[i] = (float)cref[i];
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < NT * NCOL; idx += blockDim.x)
+        Md[idx] = (float)m_entry(p.ft, crs, idx / NCOL, p.ft->acol[idx % NCOL]);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < NROI * NT; idx += blockDim.x) {
+        const int r = idx / NT, j = idx - r * NT;
+        const float k2a = k2[r] / dvr[r];
+        const float na = k2a * -1.4426950408889634f;
+        float conv = 0.f;
+        for (int c = 0; c < NCOL; c++) conv = fmaf(Md[j * NCOL + c], ex2_approx(na * c_tcol[c]), conv);
+        tac_out[idx] = fmaf(fmaf(-r1[r], k2a, k2[r]), conv, r1[r] * cr[j]);
+    }
+}
+
 __global__ void operator_kernel(const SweepParams p, int tac, double* m_out /*[54][54]*/) {
     __shared__ double crs[NGRID];
     build_crs(p.ft, p.cref + (size_t)tac * NT, crs, threadIdx.x, blockDim.x);

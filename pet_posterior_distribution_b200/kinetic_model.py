@@ -40,3 +40,29 @@ class SRTM2:
         return out[:, 0] if scalar else out
 
     __call__ = create_activity_curve
+
+
+class SRTM:
+    """GPU-backed mirror of kinetic_model.SRTM (kinetic_model.py:62-84): k2 free, reference TAC per call."""
+
+    def __init__(self, frame_time_list, frame_duration_list, device=0):
+        self._frame_time_list = np.asarray(frame_time_list, np.float64)
+        self._frame_duration_list = np.asarray(frame_duration_list, np.float64)
+        self._s = MHSampler(n_chains=1, max_tacs=1, device=device)
+        self._s.set_frames(self._frame_time_list, self._frame_duration_list)
+        self._s.set_prior(np.zeros(48), np.eye(48), np.zeros(48), np.eye(48))
+
+    def forward_model(self, DVR=None, k2=None, R1=None, tac_ref=None):
+        scalar = np.isscalar(DVR)
+        d, k, r = (np.atleast_1d(np.asarray(x, np.float64)) for x in (DVR, k2, R1))
+        n = d.size
+        if n > 48 or k.size != n or r.size != n:
+            raise ValueError("DVR, k2 and R1 must have the same length <= 48")
+        self._tac_reference = np.asarray(tac_ref, np.float64)
+        self._s.set_data(np.ones((1, 48, 54)), self._tac_reference[None], np.array([0.0]), np.ones((48, 54)))
+        dd, kk, rr = np.ones(48), np.ones(48), np.ones(48)
+        dd[:n], kk[:n], rr[:n] = d, k, r
+        out = self._s.forward_srtm(0, dd, kk, rr)[:n].T
+        return out[:, 0] if scalar else out
+
+    __call__ = forward_model

@@ -136,6 +136,13 @@ class MHSampler:
         self._ck(_lib.lib.petmh_forward(self._h, int(tac), _d(a), _d(b), _d(out)))
         return out
 
+    def forward_srtm(self, tac, DVR, k2, R1):
+        """(48,54) SRTM TAC with k2 free, == SRTM.forward_model(DVR, k2, R1, tac_ref).T (kinetic_model.py:69-84)."""
+        a, k, b = (np.ascontiguousarray(x, np.float64) for x in (DVR, k2, R1))
+        out = np.empty((N_ROI, N_FRAMES), np.float64)
+        self._ck(_lib.lib.petmh_forward_srtm(self._h, int(tac), _d(a), _d(k), _d(b), _d(out)))
+        return out
+
     def loglik(self, tac, DVR, R1):
         """(ll per ROI (48,), (logprior_DVR, logprior_R1)) of the pymc model (mcmc.py:148-155)."""
         a = np.ascontiguousarray(DVR, np.float64)

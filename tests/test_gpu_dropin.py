@@ -60,6 +60,16 @@ def test_operator_seam(forward_golden):
     assert one.shape == (54,) and np.abs(one / g["tac"][1][:, 3] - 1).max() < 1e-5
 
 
+def test_srtm_k2_free_matches_reference_golden(forward_golden):
+    """the other model of kinetic_model.py (SRTM, k2 free) vs the live reference's golden TACs."""
+    from pet_posterior_distribution_b200 import kinetic_model
+    g = forward_golden
+    k = kinetic_model.SRTM(frame_time_list=g["t"], frame_duration_list=g["dt"])
+    for c in range(3):
+        out = k.forward_model(DVR=g["DVR"][c], k2=g["k2"][c], R1=g["R1"][c], tac_ref=g["c_r"][c])
+        assert out.shape == (54, 48) and np.abs(out / g["tac_srtm"][c] - 1).max() < 1e-5
+
+
 def test_product_generator_schema(prior):
     from pet_posterior_distribution_b200 import sample_sim_data as gen
     ds = gen.generate(prior, 6, 0.1, test_style=True, seed=5)

@@ -23,6 +23,13 @@ def test_tac_matches_reference(forward_golden):
         assert np.abs(out - g["tac"][c]).max() <= 1e-12 * np.abs(g["tac"][c]).max()
 
 
+def test_srtm_k2_free_matches_reference(forward_golden):
+    g = forward_golden
+    for c in range(g["c_r"].shape[0]):
+        out = forward.srtm_tac(g["t"], g["c_r"][c], g["DVR"][c], g["k2"][c], g["R1"][c])
+        assert np.abs(out - g["tac_srtm"][c]).max() <= 1e-12 * np.abs(g["tac_srtm"][c]).max()
+
+
 def test_operator_matches_reference(forward_golden):
     g = forward_golden
     for c in range(g["c_r"].shape[0]):

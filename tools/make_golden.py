@@ -37,6 +37,7 @@ def main():
     n_case = 6
     c_r = np.empty((n_case, 54)); DVR = np.empty((n_case, 48)); R1 = np.empty((n_case, 48))
     tac = np.empty((n_case, 54, 48)); Mref = np.empty((n_case, 54, 54))
+    k2 = np.empty((n_case, 48)); tac_srtm = np.empty((n_case, 54, 48))
     k2p = np.full(n_case, float(prior["mu_k2p"]))
     for c in range(n_case):
         spread = [0.02, 0.05, 0.1, 0.2, 0.3, 0.5][c]
@@ -48,8 +49,11 @@ def main():
         model = km.SRTM2(frame_time_list=t, frame_duration_list=dt, tac_reference=c_r[c])
         tac[c] = model.create_activity_curve(DVR=DVR[c], R1=R1[c], k2p=k2p[c])
         Mref[c] = km.estimate_continuous_convolution(t, c_r[c], np.eye(54))
+        # SRTM with k2 free (kinetic_model.py:62-84), the other model of the file
+        k2[c] = np.abs(0.0126 * R1[c] * (1 + spread * rng.standard_normal(48))) + 1e-3
+        tac_srtm[c] = km.SRTM(frame_time_list=t, frame_duration_list=dt).forward_model(DVR=DVR[c], k2=k2[c], R1=R1[c], tac_ref=c_r[c])
     np.savez_compressed(os.path.join(OUT, "forward_golden.npz"), t=t, dt=dt, c_r=c_r, DVR=DVR, R1=R1,
-                        k2p=k2p, tac=tac, M=Mref)
+                        k2p=k2p, tac=tac, M=Mref, k2=k2, tac_srtm=tac_srtm)
     ds = generator.generate(prior, 4, 0.1, test_style=True, seed=7)
     np.savez_compressed(os.path.join(OUT, "dataset_s0.1.npz"),
                         varDVR=np.array(ds["varDVR"]), varR1=np.array(ds["varR1"]),
