@@ -95,3 +95,36 @@ def test_error_behaviour(dataset, prior):
         MHSampler(n_chains=0)
     with pytest.raises(ValueError):
         s.set_frames(np.zeros(10), np.zeros(10))
+
+
+def test_large_batch_shard_invariance_and_determinism(dataset, prior):
+    """Size-independent properties at a batch large enough to fill the GPU many times over
+    (8192 TACs x 16 chains = 2 M (chain, ROI) threads): same seed -> identical summaries; the batch cut
+    into two shards with global TAC offsets (what multi-GPU sharding does) -> identical rows."""
+    from pet_posterior_distribution_b200 import MHSampler
+    S, C = 8192, 16
+    k = dataset["varDVR"].shape[0]
+    idx = np.arange(S) % k
+    y = (dataset["tac_noisy_sampled"] / dataset["dt"][None, None, :]).astype(np.float32)[idx]
+    cr = dataset["vartacref"].astype(np.float32)[idx]
+    k2p = dataset["vark2p"].astype(np.float32)[idx]
+    sig = dataset["sigma_noise"].astype(np.float32)
+
+    def run(lo, hi):
+        s = MHSampler(n_chains=C, max_tacs=hi - lo, seed=77, tac_gid0=lo)
+        s.set_frames(dataset["time_vector"], dataset["dt"])
+        s.set_prior(prior["mu_DVR"], prior["Cov_DVR"], prior["mu_R1"], prior["Cov_R1"])
+        s.set_data(y[lo:hi], cr[lo:hi], k2p[lo:hi], sig)
+        s.run(draws=20, tune=100)
+        out = s.summary()
+        s.close()
+        return out
+
+    full = run(0, S)
+    assert np.isfinite(full[..., :2]).all()
+    again = run(0, S)
+    assert np.array_equal(full, again, equal_nan=True)
+    a, b = run(0, 3000), run(3000, S)                          # ragged shards
+    assert np.array_equal(np.concatenate([a, b]), full, equal_nan=True)
+    # identical data, different global TAC index -> different Philox streams -> different chains
+    assert not np.array_equal(full[0], full[k])
