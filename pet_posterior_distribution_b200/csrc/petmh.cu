@@ -563,7 +563,11 @@ extern "C" int petmh_plan(petmh_t* h, int draws, int tune, int thin) {
 static int threads_per_cta(const petmh_t* h) {
     int t = h->cfg.n_chains * 16;
     t = (t + 31) / 32 * 32;
-    return std::min(t, h->variant == 0 ? 256 : 128);
+    t = std::min(t, h->variant == 0 ? 256 : 128);
+    // small jobs (e.g. one TAC x 64 chains): spread the chains over more, smaller CTAs so that every SM gets a
+    // warp -- the sweep loop is latency-bound per warp, and an under-filled GPU has SMs to spare
+    while (t > 32 && (size_t)h->n_tac * ((h->cfg.n_chains * 16 + t - 1) / t) < 2 * 148) t /= 2;
+    return t;
 }
 
 extern "C" int petmh_advance(petmh_t* h, int n_sweeps) {

@@ -137,7 +137,7 @@ constexpr int ESS_LB = 256;
 __global__ void __launch_bounds__(ESS_LB) rd_ess(const float* xs, const float* z, const float* q05, const float* q95, int m,
                                                  int h, float* rho_scratch /*[nseg*4][h]*/, float* ess_out /*[nseg][4]*/) {
     __shared__ double sh[32];
-    __shared__ double cmean[512];
+    __shared__ double cmean[2048];
     __shared__ int s_stop, s_t;
     __shared__ double s_even, s_odd;
     const int seg = blockIdx.x >> 2, ty = blockIdx.x & 3, tid = threadIdx.x;
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(ESS_LB) rd_ess(const float* xs, const float* z
         double q = 0;
         for (int i = tid; i < h; i += blockDim.x) { const double d = series(ty, xs, z, a05, a95, base + (size_t)c * h + i) - mean; q += d * d; }
         const double v = block_sum(q, sh) / h;
-        if (tid == 0 && c < 512) cmean[c] = mean;
+        if (tid == 0 && c < 2048) cmean[c] = mean;
         sum_mean += mean; sum_mean2 += mean * mean; acov0 += v;
     }
     __syncthreads();
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(ESS_LB) rd_ess(const float* xs, const float* z
         double acc = 0.0;
         if (t < h) {
             for (int c = 0; c < m; c++) {
-                const double mu = cmean[min(c, 511)];
+                const double mu = cmean[min(c, 2047)];
                 const size_t o = base + (size_t)c * h;
                 double a = 0.0;
                 for (int n = 0; n + t < h; n++)
@@ -266,7 +266,7 @@ static inline int launch_rank_summary(const float* d_draws, int n_tac_total, int
     const int h = n_stored / 2;
     const int m = 2 * n_chains;
     const int L = m * h;
-    if (h < 4 || m > 512) return (int)cudaErrorInvalidValue;
+    if (h < 4 || m > 2048) return (int)cudaErrorInvalidValue;   // up to 1024 chains per TAC (BASELINE configs[3])
     const size_t max_elems = (size_t)1 << 27;
     int tacs_per_batch = (int)std::max<size_t>(1, max_elems / ((size_t)96 * L));
     tacs_per_batch = std::min(tacs_per_batch, n_tac_total);

@@ -62,3 +62,14 @@ def test_posterior_recovers_truth(dataset, prior):
     print("max |z| of truth:", np.abs(zs).max(), " max rhat:", sm[:, 5].max(), " min ess_bulk:", sm[:, 3].min())
     assert np.abs(zs).max() < 5.0
     assert sm[:, 5].max() < 1.2
+
+
+def test_many_chains_config4_shape(dataset, prior):
+    """BASELINE configs[3]: 1024 chains per TAC -- sampler, stored draws and rank diagnostics all handle it."""
+    s = make_sampler(dataset, prior, n_chains=1024, max_draws=100, seed=8, tacs=[2])
+    s.run(draws=6000, tune=3000, thin=60)
+    sm = s.summary()[0]
+    print("1024 chains: rhat max %.3f ess_bulk min %.0f" % (sm[:, 5].max(), sm[:, 3].min()))
+    assert np.isfinite(sm[:, :6]).all() and (sm[:, 3] > 100).all() and sm[:, 5].max() < 1.5
+    dvr, _ = s.chains()
+    assert dvr.shape == (1, 1024, 100, 48)
