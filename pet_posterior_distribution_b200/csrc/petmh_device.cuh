@@ -260,11 +260,11 @@ __device__ __forceinline__ u64 trunc_factor2(const u64 zp) {
     return fadd2(one, pack2(-m0, -m1));
 }
 
-// prod_t s_t (1 - erfc(z_t)/2)^2 over NP frame pairs (packed even/odd partial products).  The erfc factor is skipped
+// log2 of prod_t s_t (1 - erfc(z_t)/2)^2 over NP frame pairs.  The erfc factor is skipped
 // warp-uniformly when every lane has z >= Z_CUT; whether it applies to a given element depends
 // on that element's z alone (branch-free select), never on neighbouring lanes.
 template <int NP>
-__device__ __forceinline__ u64 trunc_prod(const u64 (&sp)[2], const u64 (&zp)[2]) {
+__device__ __forceinline__ float trunc_log2(const u64 (&sp)[2], const u64 (&zp)[2]) {
     float z0, z1, z2, z3;
     unpack2(zp[0], z0, z1);
     float zmin = fminf(z0, z1);
@@ -280,7 +280,9 @@ __device__ __forceinline__ u64 trunc_prod(const u64 (&sp)[2], const u64 (&zp)[2]
     } else if (NP == 2) {
         prp = fmul2(prp, sp[1]);
     }
-    return prp;   // packed partial products (even / odd frames); the caller takes one lg2 per row block
+    float pa, pb;
+    unpack2(prp, pa, pb);
+    return lg2_approx(pa * pb);
 }
 
 template <int VARIANT>
@@ -392,10 +394,6 @@ __device__ __noinline__ float3 eval3(const int l16, const float d0, const float 
                     tac_out[it * NT + blk * RB + 2 * pq + 1] = fmaf(coef0, c1, r10 * crb[2 * pq + 1]);
                 }
             }
-            // running product of the block's 18 frames: s in [~5e-3, ~50] for any state that can be accepted, so
-            // 18 factors stay far inside the fp32 range; a hopeless state may overflow / underflow to inf / 0,
-            // which makes the log-likelihood non-finite and the move rejected -- the reference's decision too
-            u64 prodp = pack2(1.0f, 1.0f);
 #pragma unroll
             for (int g = 0; g < 5; g++) {
                 u64 sp[2], zp[2];
@@ -406,20 +404,15 @@ __device__ __noinline__ float3 eval3(const int l16, const float d0, const float 
                     const float2 cb = *reinterpret_cast<const float2*>(crb + 4 * g + 2);
                     frame_pair(acc0[2 * g], pack2(ca.x, ca.y), pack2(cv.x, cv.y), pack2(yv.x, yv.y), coefd, r1d, G0, sp[0], zp[0]);
                     frame_pair(acc0[2 * g + 1], pack2(cb.x, cb.y), pack2(cv.z, cv.w), pack2(yv.z, yv.w), coefd, r1d, G0, sp[1], zp[1]);
-                    prodp = fmul2(prodp, trunc_prod<2>(sp, zp));
+                    S0 += trunc_log2<2>(sp, zp);
                 } else {
                     const float2 cv = *reinterpret_cast<const float2*>(crow + 16);
                     const float2 yv = *reinterpret_cast<const float2*>(yrow + 16);
                     const float2 ca = *reinterpret_cast<const float2*>(crb + 16);
                     frame_pair(acc0[8], pack2(ca.x, ca.y), pack2(cv.x, cv.y), pack2(yv.x, yv.y), coefd, r1d, G0, sp[0], zp[0]);
                     sp[1] = zp[1] = 0ull;
-                    prodp = fmul2(prodp, trunc_prod<1>(sp, zp));
+                    S0 += trunc_log2<1>(sp, zp);
                 }
-            }
-            {
-                float pa, pb;
-                unpack2(prodp, pa, pb);
-                S0 += lg2_approx(pa * pb);
             }
             // rotate item registers: (0,1,2) <- (1,2,0)
 #pragma unroll
