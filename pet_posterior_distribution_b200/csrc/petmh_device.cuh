@@ -160,7 +160,10 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // ------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011); bit-exact with oracle/philox.py
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#ifndef PETMH_PHILOX_INLINE
+#define PETMH_PHILOX_INLINE __forceinline__
+#endif
+__device__ PETMH_PHILOX_INLINE uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll
     for (int r = 0; r < 10; r++) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
