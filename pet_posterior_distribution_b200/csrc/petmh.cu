@@ -54,6 +54,7 @@ struct petmh_handle {
     // schedule
     int plan_draws = 0, plan_tune = 0, plan_thin = 1;
     int sweep = 0;
+    bool state_ready = false;     // petmh_reset / petmh_set_state called
     int mom_n[2] = {0, 0};        // draws merged per half
     int mom_launches[2] = {0, 0}; // launches per half (each contributes nb-1 lag terms)
     // scratch for hooks
@@ -546,6 +547,7 @@ extern "C" int petmh_reset(petmh_t* h) {
     init_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_q, h->d_scale, h->d_cnt, h->d_nacc, h->d_mom, h->d_mu, NC);
     CU(cudaGetLastError());
     h->sweep = 0;
+    h->state_ready = true;
     h->mom_n[0] = h->mom_n[1] = 0;
     h->mom_launches[0] = h->mom_launches[1] = 0;
     return PETMH_OK;
@@ -574,6 +576,7 @@ extern "C" int petmh_advance(petmh_t* h, int n_sweeps) {
     int rc = check_ready(h);
     if (rc) return rc;
     if (n_sweeps < 0) return fail(h, PETMH_EINVAL, "n_sweeps < 0");
+    if (!h->state_ready) return fail(h, PETMH_EINVAL, "chain state not initialised: call petmh_reset, petmh_run or petmh_set_state first");
     CU(cudaSetDevice(h->cfg.device));
     const int nthr = threads_per_cta(h);
     const int chains_per_cta = nthr / 16;
@@ -717,6 +720,7 @@ extern "C" int petmh_set_state(petmh_t* h, const float* q, const float* scale, i
     CU(cudaMemsetAsync(h->d_mom, 0, NCall * 96 * 6 * sizeof(float), h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->sweep = sweep;
+    h->state_ready = true;
     h->mom_n[0] = h->mom_n[1] = 0;
     h->mom_launches[0] = h->mom_launches[1] = 0;
     return PETMH_OK;

@@ -91,6 +91,12 @@ def test_error_behaviour(dataset, prior):
         s.set_data(y[:1], dataset["vartacref"][:1], dataset["vark2p"][:1], None)
     with pytest.raises(PetmhError):                                 # not positive definite
         s.set_prior(prior["mu_DVR"], -np.eye(48), prior["mu_R1"], prior["Cov_R1"])
+    ok = make_sampler(dataset, prior, n_chains=2, tacs=[0])
+    ok.plan(10, 10)
+    with pytest.raises(PetmhError):                                 # advance before reset / set_state
+        ok.advance(5)
+    ok.reset()
+    ok.advance(5)
     with pytest.raises(PetmhError):
         MHSampler(n_chains=0)
     with pytest.raises(ValueError):
