@@ -154,3 +154,35 @@ def test_run_reproducible_and_chunking(dataset, prior):
     c = make_sampler(dataset, prior, n_chains=4, max_draws=40, seed=100, tacs=[0, 1])
     c.run(draws=40, tune=100)
     assert not np.array_equal(c.chains()[0], da)
+
+
+@pytest.mark.parametrize("mean_sigma", [0.05, 0.2])
+def test_taped_decisions_other_noise_levels(prior, dataset, mean_sigma):
+    """BASELINE configs[3] noise sweep: sigma 0.05 (little truncation) and 0.2 (the erfc term matters in many
+    frames): decisions on a shared tape still match the fp64 oracle on data from the GPU generator."""
+    from oracle import mh
+    from oracle.logp import Model
+    from pet_posterior_distribution_b200 import MHSampler
+    from pet_posterior_distribution_b200 import sample_sim_data as gen
+    t, dt = gen.frame_grid()
+    sig = gen.noise_table(np.random.default_rng(3), mean_sigma, t, dt)
+    s = MHSampler(n_chains=2, max_tacs=2, seed=1)
+    s.set_frames(t, dt)
+    s.set_prior(prior["mu_DVR"], prior["Cov_DVR"], prior["mu_R1"], prior["Cov_R1"])
+    s.synth(2, 99, prior["mu_tac_ref"], prior["Cov_tac_ref"], float(prior["mu_k2p"]), sig)
+    g = s.synth_get()
+    n_sweeps, tune = 250, 200
+    rng = np.random.default_rng(13)
+    tapes = [mh.Tape.random(n_sweeps, rng) for _ in range(2)]
+    out = s.run_taped(1, np.stack([x.normals for x in tapes]), np.stack([x.logu for x in tapes]),
+                      np.stack([x.rank for x in tapes]), tune)
+    m = Model(t, g["tac_ref"][1], float(prior["mu_k2p"]), g["y"][1].astype(np.float64), sig,
+              prior["mu_DVR"], prior["Cov_DVR"], prior["mu_R1"], prior["Cov_R1"])
+    total = agree = 0
+    for c in range(2):
+        ref = mh.run_chain(m, tapes[c], tune, n_sweeps - tune, mode="lean", forced_draws=out["draws"][c])
+        dec = ~ref["undecidable"]
+        total += dec.sum()
+        agree += (ref["accept"][dec] == ref["forced_accept"][dec]).sum()
+    print("sigma %.2f: decisions %d agree %d" % (mean_sigma, total, agree))
+    assert agree >= 0.9999 * total
