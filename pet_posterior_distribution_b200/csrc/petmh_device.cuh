@@ -344,7 +344,7 @@ __device__ __noinline__ float3 eval3(const int l16, const float d0, const float 
             PETMH_LOADCOL(ma, Mp)
             PETMH_EXPS(ea, 0)
             int c = 0;
-#pragma unroll 1
+#pragma unroll 2
             for (; c + 1 < n0; c += 2) {
                 PETMH_LOADCOL(mb, Mp + (RSTRIDE / 4))
                 PETMH_EXPS(eb, c + 1)
