@@ -288,7 +288,9 @@ __device__ __forceinline__ float trunc_log2(const u64 (&sp)[2], const u64 (&zp)[
     return lg2_approx(pa * pb);
 }
 
-template <int VARIANT>
+// HOOK = true only in the parity-hook / generator kernels (writes the unclamped TAC to tac_out); the sweep kernel's
+// instance carries no hook code (hot-code size matters: the kernel is sensitive to instruction-cache misses).
+template <int VARIANT, bool HOOK = false>
 __device__ __noinline__ float3 eval3(const int l16, const float d0, const float d1, const float d2, const float a0,
                                      const float a1, const float a2, float* tac_out) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -388,7 +390,7 @@ __device__ __noinline__ float3 eval3(const int l16, const float d0, const float 
             const float* yrow = sYcc + rowoff0 + blk * RSTRIDE;
             const float* crow = sCc + rowoff0 + blk * RSTRIDE;
             const u64 coefd = pack2(coef0, coef0), r1d = pack2(r10, r10);
-            if (tac_out != nullptr) {   // parity hook only (warp-uniform): the unclamped TAC
+            if (HOOK) {   // parity hook only: the unclamped TAC
 #pragma unroll
                 for (int pq = 0; pq < NPAIR; pq++) {
                     float c0, c1;
@@ -820,7 +822,7 @@ __global__ void forward_kernel(const SweepParams p, int tac, const float* dvr, c
             b[s] = r1[roi[s]];
         }
         float* scratch = reinterpret_cast<float*>(smem + SM_STATE) + tid * SLOTS * NT;
-        const float3 v = eval3<0>(l16, a[0], a[1], a[2], b[0], b[1], b[2], scratch);
+        const float3 v = eval3<0, true>(l16, a[0], a[1], a[2], b[0], b[1], b[2], scratch);
         ll[0] = v.x; ll[1] = v.y; ll[2] = v.z;
         if (tid < 16) {
 #pragma unroll

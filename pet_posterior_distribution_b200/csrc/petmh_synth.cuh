@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(64) synth_kernel(const SweepParams p, const Sy
         load_tac_image(p, tac, smem, tid, 64);
         if (tid < 32) {
             const int l16 = tid & 15;
-            eval3<0>(l16, (float)xv[0][l16], (float)xv[0][l16 + 16], (float)xv[0][l16 + 32], (float)xv[1][l16],
+            eval3<0, true>(l16, (float)xv[0][l16], (float)xv[0][l16 + 16], (float)xv[0][l16 + 32], (float)xv[1][l16],
                      (float)xv[1][l16 + 16], (float)xv[1][l16 + 32], scratch + tid * SLOTS * NT);
         }
         __syncthreads();
