@@ -279,15 +279,16 @@ static inline int launch_rank_summary(const float* d_draws, int n_tac_total, int
     size_t tmp_bytes = 0;
     cudaError_t e = cudaSuccess;
 #define RD(call) do { e = (call); if (e != cudaSuccess) goto done; } while (0)
-    RD(cudaMalloc(&xs, nmax * 4)); RD(cudaMalloc(&z, nmax * 4)); RD(cudaMalloc(&zf, nmax * 4));
-    RD(cudaMalloc(&k0, nmax * 8)); RD(cudaMalloc(&k1, nmax * 8)); RD(cudaMalloc(&v0, nmax * 4)); RD(cudaMalloc(&v1, nmax * 4));
-    RD(cudaMalloc(&med, nseg_b * 4)); RD(cudaMalloc(&q05, nseg_b * 4)); RD(cudaMalloc(&q95, nseg_b * 4));
-    RD(cudaMalloc(&rho, nseg_b * 4 * (size_t)h * 4)); RD(cudaMalloc(&ess, nseg_b * 4 * 4)); RD(cudaMalloc(&rhat, nseg_b * 4));
+    // stream-ordered allocations: the handle keeps the pool cached, so repeated summaries do not pay cudaMalloc/cudaFree
+    RD(cudaMallocAsync(&xs, nmax * 4, st)); RD(cudaMallocAsync(&z, nmax * 4, st)); RD(cudaMallocAsync(&zf, nmax * 4, st));
+    RD(cudaMallocAsync(&k0, nmax * 8, st)); RD(cudaMallocAsync(&k1, nmax * 8, st)); RD(cudaMallocAsync(&v0, nmax * 4, st)); RD(cudaMallocAsync(&v1, nmax * 4, st));
+    RD(cudaMallocAsync(&med, nseg_b * 4, st)); RD(cudaMallocAsync(&q05, nseg_b * 4, st)); RD(cudaMallocAsync(&q95, nseg_b * 4, st));
+    RD(cudaMallocAsync(&rho, nseg_b * 4 * (size_t)h * 4, st)); RD(cudaMallocAsync(&ess, nseg_b * 4 * 4, st)); RD(cudaMallocAsync(&rhat, nseg_b * 4, st));
     {
         int seg_bits = 1;
         while (((size_t)1 << seg_bits) < nseg_b) seg_bits++;
         RD(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k0, k1, v0, v1, nmax, 0, 32 + seg_bits, st));
-        RD(cudaMalloc(&tmp, tmp_bytes));
+        RD(cudaMallocAsync(&tmp, tmp_bytes, st));
         for (int t0 = 0; t0 < n_tac_total; t0 += tacs_per_batch) {
             RankDiagParams p{d_draws, n_chains, max_draws, n_stored, t0, std::min(tacs_per_batch, n_tac_total - t0), h, L};
             const int nseg = p.n_tac * 96;
@@ -309,8 +310,11 @@ static inline int launch_rank_summary(const float* d_draws, int n_tac_total, int
     }
 done:
 #undef RD
-    cudaFree(xs); cudaFree(z); cudaFree(zf); cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1); cudaFree(med);
-    cudaFree(q05); cudaFree(q95); cudaFree(rho); cudaFree(ess); cudaFree(rhat); cudaFree(tmp);
+    {
+        void* bufs[] = {xs, z, zf, k0, k1, v0, v1, med, q05, q95, rho, ess, rhat, tmp};
+        for (void* b : bufs) if (b) cudaFreeAsync(b, st);
+        cudaStreamSynchronize(st);
+    }
     return (int)e;
 }
 
