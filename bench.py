@@ -319,8 +319,8 @@ def run_b200(args):
             "gpu_launches": launches,
             "roofline": {"bound": "fp32", "achieved": ach, "peak": peak_fp32, "unit": "TFLOP/s", "frac": ach / peak_fp32,
                          # dram__bytes_read+write of one mh_sweep_kernel launch at the default workload
-                         # (131072 TACs x 16 chains, 50 sweeps), ncu capture profiles/r01_ncu_sweep_dram_bench.csv
-                         "traffic": 18139866624 if (S == 131072 and SW == 50) else None,   # (measured at 50 sweeps per launch)
+                         # (131072 TACs x 16 chains, 100 sweeps), ncu capture profiles/r01_ncu_sweep_dram_bench.csv
+                         "traffic": 18610574336 if (S == 131072 and SW == 100) else None,
                          "note": "dominant kernel mh_sweep_kernel (%.1f %% of the step by CUDA events on its stream); achieved = "
                                  "3980 algorithmic FP32 flop/chain-step x per-GPU kernel rate; peak = 148 SM x 128 lanes x 2 x SM clock "
                                  "under load (nominal formula: MEASURED_PEAKS.json has no FP32 figure)" % (100 * dev_s / wall_s),
