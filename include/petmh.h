@@ -130,7 +130,7 @@ int petmh_get_chains(petmh_t* h, float* dvr, float* r1);
 /* out[n_tac][96][PETMH_N_STATS] f32: mean, sd, mcse_mean, ess_bulk, ess_tail, r_hat,
  * accept_rate, scaling -- from stored draws when max_draws > 0 (rank-normalised split
  * R-hat / ESS as ArviZ), else from running split-half moments (classic split R-hat,
- * batch-means ESS; ess_tail = NaN). */
+ * lag-1 (AR(1)) effective sample size; ess_tail = NaN). */
 int petmh_get_summary(petmh_t* h, float* out);
 /* same, written to a DEVICE buffer (e.g. a slice of an NCCL all-gather buffer) on
  * `stream` (a cudaStream_t, 0 = the handle's). */

@@ -634,36 +634,40 @@ extern "C" int petmh_run_taped(petmh_t* h, int tac, int n_tape_chains, int n_swe
     const size_t n = (size_t)n_tape_chains * n_sweeps * 96;
     float *dn = nullptr, *dl = nullptr, *dd = nullptr, *ddelta = nullptr, *dscale = nullptr;
     uint8_t *dr = nullptr, *dacc = nullptr;
-    CU(cudaMalloc(&dn, n * 4)); CU(cudaMalloc(&dl, n * 4)); CU(cudaMalloc(&dr, n));
-    CU(cudaMalloc(&dd, n * 4)); CU(cudaMalloc(&ddelta, n * 4)); CU(cudaMalloc(&dacc, n));
-    CU(cudaMalloc(&dscale, (size_t)n_tape_chains * 96 * 4));
-    CU(cudaMemcpyAsync(dn, normals, n * 4, cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(dl, logu, n * 4, cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(dr, rank, n, cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemsetAsync(ddelta, 0, n * 4, h->stream));
-    CU(cudaMemsetAsync(dacc, 0, n, h->stream));
-    SweepParams p = base_params(h);
-    p.n_chains = n_tape_chains;
-    p.scale = dscale;
-    p.draws = nullptr;
-    p.sweep0 = 0;
-    p.n_sweeps = n_sweeps;
-    p.tune_until = tune;
-    p.tape_n = dn; p.tape_logu = dl; p.tape_rank = dr;
-    p.dbg_draws = dd; p.dbg_delta = ddelta; p.dbg_accept = dacc;
-    p.tape_tac = tac; p.tape_sweeps = n_sweeps;
-    int nthr = std::min(256, (n_tape_chains * 16 + 31) / 32 * 32);
-    const int cpc = nthr / 16;
-    const unsigned grid = (unsigned)((n_tape_chains + cpc - 1) / cpc);
-    mh_sweep_kernel<0, true><<<grid, nthr, smem_bytes(nthr), h->stream>>>(p);
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(draws_out, dd, n * 4, cudaMemcpyDeviceToHost, h->stream));
-    if (delta_out) CU(cudaMemcpyAsync(delta_out, ddelta, n * 4, cudaMemcpyDeviceToHost, h->stream));
-    if (accept_out) CU(cudaMemcpyAsync(accept_out, dacc, n, cudaMemcpyDeviceToHost, h->stream));
-    if (scale_out) CU(cudaMemcpyAsync(scale_out, dscale, (size_t)n_tape_chains * 96 * 4, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    cudaFree(dn); cudaFree(dl); cudaFree(dr); cudaFree(dd); cudaFree(ddelta); cudaFree(dacc); cudaFree(dscale);
-    return PETMH_OK;
+    auto body = [&]() -> int {
+        CU(cudaMalloc(&dn, n * 4)); CU(cudaMalloc(&dl, n * 4)); CU(cudaMalloc(&dr, n));
+        CU(cudaMalloc(&dd, n * 4)); CU(cudaMalloc(&ddelta, n * 4)); CU(cudaMalloc(&dacc, n));
+        CU(cudaMalloc(&dscale, (size_t)n_tape_chains * 96 * 4));
+        CU(cudaMemcpyAsync(dn, normals, n * 4, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(dl, logu, n * 4, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(dr, rank, n, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemsetAsync(ddelta, 0, n * 4, h->stream));
+        CU(cudaMemsetAsync(dacc, 0, n, h->stream));
+        SweepParams p = base_params(h);
+        p.n_chains = n_tape_chains;
+        p.scale = dscale;
+        p.draws = nullptr;
+        p.sweep0 = 0;
+        p.n_sweeps = n_sweeps;
+        p.tune_until = tune;
+        p.tape_n = dn; p.tape_logu = dl; p.tape_rank = dr;
+        p.dbg_draws = dd; p.dbg_delta = ddelta; p.dbg_accept = dacc;
+        p.tape_tac = tac; p.tape_sweeps = n_sweeps;
+        const int nthr = std::min(256, (n_tape_chains * 16 + 31) / 32 * 32);
+        const int cpc = nthr / 16;
+        const unsigned grid = (unsigned)((n_tape_chains + cpc - 1) / cpc);
+        mh_sweep_kernel<0, true><<<grid, nthr, smem_bytes(nthr), h->stream>>>(p);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(draws_out, dd, n * 4, cudaMemcpyDeviceToHost, h->stream));
+        if (delta_out) CU(cudaMemcpyAsync(delta_out, ddelta, n * 4, cudaMemcpyDeviceToHost, h->stream));
+        if (accept_out) CU(cudaMemcpyAsync(accept_out, dacc, n, cudaMemcpyDeviceToHost, h->stream));
+        if (scale_out) CU(cudaMemcpyAsync(scale_out, dscale, (size_t)n_tape_chains * 96 * 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        return PETMH_OK;
+    };
+    rc = body();
+    cudaFree(dn); cudaFree(dl); cudaFree(dr); cudaFree(dd); cudaFree(ddelta); cudaFree(dacc); cudaFree(dscale);   // also on error paths
+    return rc;
 }
 
 // ---- outputs ---------------------------------------------------------------------------
