@@ -71,6 +71,26 @@ def _summarise_clocks(lines):
 # chain-step, each a resample-convolve-interpolate forward call: the work pymc's delta_logp +
 # CreateTAC_SRTM2.perform do), one chain per process on all host cores.
 # ----------------------------------------------------------------------------------------------
+def _cpu_lean_c(sweeps, cores):
+    """Restructured CPU baseline: the C oracle (oracle/c/mh_oracle.c, fp64, operator form, cached per-ROI log-lik,
+    incremental prior), one chain per host thread."""
+    import numpy as _np
+    from oracle import cmh
+    from oracle.logp import Model
+    g = os.path.join(ROOT, "tests", "golden")
+    pr = _np.load(os.path.join(g, "prior_stats_nROI48.npz"))
+    ds = _np.load(os.path.join(g, "dataset_s0.1.npz"))
+    y = ds["tac_noisy_sampled"][0] / ds["dt"][None, :]
+    m = Model(ds["time_vector"], ds["vartacref"][0], ds["vark2p"][0], y, ds["sigma_noise"],
+              pr["mu_DVR"], pr["Cov_DVR"], pr["mu_R1"], pr["Cov_R1"])
+    cm = cmh.CModel(m)
+    cm.run_free(cores, 1, 1, keep=False, threads=cores)
+    t0 = time.perf_counter()
+    cm.run_free(cores, sweeps, 0, seed=3, keep=False, threads=cores)
+    dt = time.perf_counter() - t0
+    return cores * sweeps * 96 / dt, dt
+
+
 def _cpu_worker(args):
     seed, sweeps, mode = args
     os.environ["OMP_NUM_THREADS"] = "1"
@@ -113,12 +133,16 @@ def run_reference(args):
     cores = os.cpu_count()
     sweeps = args.ref_sweeps
     pool = mp.get_context("fork").Pool(cores)
-    for _ in range(args.warmup):
-        cpu_rate(1, args.ref_mode, cores, pool)
     times = []
-    for _ in range(args.steps):
-        _, dt = cpu_rate(sweeps, args.ref_mode, cores, pool)
-        times.append(dt)
+    if args.ref_mode == "lean":
+        for _ in range(args.steps):
+            times.append(_cpu_lean_c(sweeps, cores)[1])
+    else:
+        for _ in range(args.warmup):
+            cpu_rate(1, args.ref_mode, cores, pool)
+        for _ in range(args.steps):
+            _, dt = cpu_rate(sweeps, args.ref_mode, cores, pool)
+            times.append(dt)
     pool.close()
     total = sum(times)
     value = cores * sweeps * 96 * args.steps / total
@@ -294,10 +318,10 @@ def run_b200(args):
                                    env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
                 return json.loads(r.stdout.strip().splitlines()[-1])
             jf = child("faithful", args.cpu_sweeps)
-            jl = child("lean", args.cpu_sweeps * 40)
+            jl = child("lean", args.cpu_sweeps * 400)
             cpu = {"value": jf["value"], "unit": "chain-steps/s", "cores": jf["cpu_baseline"]["cores"], "kind": "port",
                    "sample": jf["cpu_baseline"]["sample"], "restructured_cpu_value": jl["value"],
-                   "restructured_cpu_note": "lean oracle (operator M, cached per-ROI log-lik, incremental prior), same cores"}
+                   "restructured_cpu_note": "C oracle oracle/c/mh_oracle.c (operator M, cached per-ROI log-lik, incremental prior, fp64, libm), one chain per core, same cores"}
         except Exception as e:          # pragma: no cover
             cpu = {"value": None, "unit": "chain-steps/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
         line = {

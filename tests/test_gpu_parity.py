@@ -186,3 +186,31 @@ def test_taped_decisions_other_noise_levels(prior, dataset, mean_sigma):
         agree += (ref["accept"][dec] == ref["forced_accept"][dec]).sum()
     print("sigma %.2f: decisions %d agree %d" % (mean_sigma, total, agree))
     assert agree >= 0.9999 * total
+
+
+def test_taped_decisions_large_sample(dataset, prior, models):
+    """>= 99.99 % identical decisions on a large sample: 16 chains x 1500 sweeps = 2.3 M chain-steps replayed by the
+    C oracle (fp64) under teacher forcing; also reports the worst |Delta_gpu - Delta_fp64| near the threshold."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import cmh, mh
+    s = make_sampler(dataset, prior)
+    n_sweeps, tune, n_chains, tac = 1500, 1000, 16, 2
+    rng = np.random.default_rng(101)
+    tapes = [mh.Tape.random(n_sweeps, rng) for _ in range(n_chains)]
+    out = s.run_taped(tac, np.stack([t.normals for t in tapes]), np.stack([t.logu for t in tapes]),
+                      np.stack([t.rank for t in tapes]), tune)
+    cm = cmh.CModel(models[tac])
+    with ThreadPoolExecutor(8) as ex:
+        refs = list(ex.map(lambda c: cm.run_forced(tapes[c], tune, n_sweeps - tune, out["draws"][c]), range(n_chains)))
+    total = agree = 0
+    worst = 0.0
+    for c, ref in enumerate(refs):
+        dec = ~ref["undecidable"]
+        total += int(dec.sum())
+        agree += int((ref["accept"][dec] == ref["forced_accept"][dec]).sum())
+        near = np.isfinite(ref["delta"]) & (np.abs(ref["delta"]) < 30)
+        worst = max(worst, float(np.abs(out["delta"][c][near] - ref["delta"][near]).max()))
+        assert np.array_equal(out["scale"][c], ref["scale"])
+    flips = total - agree
+    print("decisions %d, flips %d (%.2e), max |dDelta| for |Delta|<30: %.2e" % (total, flips, flips / total, worst))
+    assert agree >= 0.9999 * total
