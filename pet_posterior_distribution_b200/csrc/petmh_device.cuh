@@ -387,16 +387,21 @@ __device__ __noinline__ float3 eval3(const int l16, const float d0, const float 
         const float* crb = sCr + blk * RB;
 #pragma unroll 1
         for (int it = 0; it < K; it++) {   // (fully unrolling this loop was measured slower: code size)
-            const float* yrow = sYcc + rowoff0 + blk * RSTRIDE;
-            const float* crow = sCc + rowoff0 + blk * RSTRIDE;
-            const u64 coefd = pack2(coef0, coef0), r1d = pack2(r10, r10);
+#define PETMH_SEL(x0, x1, x2) (it == 0 ? (x0) : (it == 1 ? (x1) : (x2)))
+            const int rowoff = PETMH_SEL(rowoff0, rowoff1, rowoff2);
+            const float coefi = PETMH_SEL(coef0, coef1, coef2), r1i = PETMH_SEL(r10, r11, r12);
+            const float* yrow = sYcc + rowoff + blk * RSTRIDE;
+            const float* crow = sCc + rowoff + blk * RSTRIDE;
+            const u64 coefd = pack2(coefi, coefi), r1d = pack2(r1i, r1i);
+            u64 Gi = 0ull;
+            float Si = 0.f;
             if (HOOK) {   // parity hook only: the unclamped TAC
 #pragma unroll
                 for (int pq = 0; pq < NPAIR; pq++) {
                     float c0, c1;
-                    unpack2(acc0[pq], c0, c1);
-                    tac_out[it * NT + blk * RB + 2 * pq] = fmaf(coef0, c0, r10 * crb[2 * pq]);
-                    tac_out[it * NT + blk * RB + 2 * pq + 1] = fmaf(coef0, c1, r10 * crb[2 * pq + 1]);
+                    unpack2(PETMH_SEL(acc0[pq], acc1[pq], acc2[pq]), c0, c1);
+                    tac_out[it * NT + blk * RB + 2 * pq] = fmaf(coefi, c0, r1i * crb[2 * pq]);
+                    tac_out[it * NT + blk * RB + 2 * pq + 1] = fmaf(coefi, c1, r1i * crb[2 * pq + 1]);
                 }
             }
 #pragma unroll
@@ -407,26 +412,22 @@ __device__ __noinline__ float3 eval3(const int l16, const float d0, const float 
                     const float4 yv = *reinterpret_cast<const float4*>(yrow + 4 * g);
                     const float2 ca = *reinterpret_cast<const float2*>(crb + 4 * g);
                     const float2 cb = *reinterpret_cast<const float2*>(crb + 4 * g + 2);
-                    frame_pair(acc0[2 * g], pack2(ca.x, ca.y), pack2(cv.x, cv.y), pack2(yv.x, yv.y), coefd, r1d, G0, sp[0], zp[0]);
-                    frame_pair(acc0[2 * g + 1], pack2(cb.x, cb.y), pack2(cv.z, cv.w), pack2(yv.z, yv.w), coefd, r1d, G0, sp[1], zp[1]);
-                    S0 += trunc_log2<2>(sp, zp);
+                    frame_pair(PETMH_SEL(acc0[2 * g], acc1[2 * g], acc2[2 * g]), pack2(ca.x, ca.y), pack2(cv.x, cv.y), pack2(yv.x, yv.y), coefd, r1d, Gi, sp[0], zp[0]);
+                    frame_pair(PETMH_SEL(acc0[2 * g + 1], acc1[2 * g + 1], acc2[2 * g + 1]), pack2(cb.x, cb.y), pack2(cv.z, cv.w), pack2(yv.z, yv.w), coefd, r1d, Gi, sp[1], zp[1]);
+                    Si += trunc_log2<2>(sp, zp);
                 } else {
                     const float2 cv = *reinterpret_cast<const float2*>(crow + 16);
                     const float2 yv = *reinterpret_cast<const float2*>(yrow + 16);
                     const float2 ca = *reinterpret_cast<const float2*>(crb + 16);
-                    frame_pair(acc0[8], pack2(ca.x, ca.y), pack2(cv.x, cv.y), pack2(yv.x, yv.y), coefd, r1d, G0, sp[0], zp[0]);
+                    frame_pair(PETMH_SEL(acc0[8], acc1[8], acc2[8]), pack2(ca.x, ca.y), pack2(cv.x, cv.y), pack2(yv.x, yv.y), coefd, r1d, Gi, sp[0], zp[0]);
                     sp[1] = zp[1] = 0ull;
-                    S0 += trunc_log2<1>(sp, zp);
+                    Si += trunc_log2<1>(sp, zp);
                 }
             }
-            // rotate item registers: (0,1,2) <- (1,2,0)
-#pragma unroll
-            for (int pq = 0; pq < NPAIR; pq++) { const u64 t_ = acc0[pq]; acc0[pq] = acc1[pq]; acc1[pq] = acc2[pq]; acc2[pq] = t_; }
-            { const float t_ = coef0; coef0 = coef1; coef1 = coef2; coef2 = t_; }
-            { const float t_ = r10; r10 = r11; r11 = r12; r12 = t_; }
-            { const u64 t_ = G0; G0 = G1; G1 = G2; G2 = t_; }
-            { const float t_ = S0; S0 = S1; S1 = S2; S2 = t_; }
-            { const int t_ = rowoff0; rowoff0 = rowoff1; rowoff1 = rowoff2; rowoff2 = t_; }
+            if (it == 0) { G0 = fadd2(G0, Gi); S0 += Si; }
+            else if (it == 1) { G1 = fadd2(G1, Gi); S1 += Si; }
+            else { G2 = fadd2(G2, Gi); S2 += Si; }
+#undef PETMH_SEL
         }
     }
     const unsigned char* bad = smem + SM_BAD;
