@@ -222,9 +222,7 @@ constexpr int K = SLOTS;
 // Two consecutive frames of one item in packed fp32x2 arithmetic (FMUL2 / FFMA2):
 // TAC assembly (kinetic_model.py:157-158), clamp (mcmc.py:152), Gaussian term, z = sqrt(s)/(sig sqrt2).
 //   convp = {conv_f, conv_f+1}, crp = c_r pair, ccp = 1/(sig sqrt2) pair, nyp = -(y/(sig sqrt2)) pair
-__device__ __forceinline__ void frame_pair(const u64 convp, const u64 crp, const u64 ccp, const u64 nyp, const u64 coefd,
-                                           const u64 r1d, u64& Gp, u64& sp, u64& zp) {
-    const u64 raw = ffma2r(convp, coefd, fmul2(crp, r1d));
+__device__ __forceinline__ void frame_pair(const u64 raw, const u64 ccp, const u64 nyp, u64& Gp, u64& sp, u64& zp) {
     float s0, s1;
     unpack2(raw, s0, s1);
     s0 = s0 < 0.f ? 1e-6f : s0;
@@ -299,8 +297,7 @@ __device__ __noinline__ float3 eval3(const int l16, const float d0, const float 
     const float k2p = sCr[K2P_SLOT];
     // rotating per-item registers: slot 0 is the item being processed by the likelihood loop
     float na0, na1, na2, coef0, coef1, coef2, r10 = a0, r11 = a1, r12 = a2;
-    u64 G0 = 0ull, G1 = 0ull, G2 = 0ull;   // Gaussian term, packed partial sums (even / odd frames)
-    float S0 = 0.f, S1 = 0.f, S2 = 0.f;
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f;   // per-item log-likelihood, accumulated over the row blocks
     {
         const float k20 = k2p * a0, k21 = k2p * a1, k22 = k2p * a2;   // kinetic_model.py:153
         const float k2a0 = k20 / d0, k2a1 = k21 / d1, k2a2 = k22 / d2; // :154
@@ -390,18 +387,37 @@ __device__ __noinline__ float3 eval3(const int l16, const float d0, const float 
 #define PETMH_SEL(x0, x1, x2) (it == 0 ? (x0) : (it == 1 ? (x1) : (x2)))
             const int rowoff = PETMH_SEL(rowoff0, rowoff1, rowoff2);
             const float coefi = PETMH_SEL(coef0, coef1, coef2), r1i = PETMH_SEL(r10, r11, r12);
+#undef PETMH_SEL
             const float* yrow = sYcc + rowoff + blk * RSTRIDE;
             const float* crow = sCc + rowoff + blk * RSTRIDE;
             const u64 coefd = pack2(coefi, coefi), r1d = pack2(r1i, r1i);
+            // unclamped TAC of the item's 18 frames: R1 c_r + coef conv (kinetic_model.py:157).  `it` is uniform:
+            // one short branch per item picks the accumulator set (no register rotation, no per-pair selects)
+            u64 raw[NPAIR];
+#pragma unroll
+            for (int pq = 0; pq < NPAIR; pq++) {
+                const float2 c = *reinterpret_cast<const float2*>(crb + 2 * pq);
+                raw[pq] = fmul2(pack2(c.x, c.y), r1d);
+            }
+            if (it == 0) {
+#pragma unroll
+                for (int pq = 0; pq < NPAIR; pq++) raw[pq] = ffma2r(acc0[pq], coefd, raw[pq]);
+            } else if (it == 1) {
+#pragma unroll
+                for (int pq = 0; pq < NPAIR; pq++) raw[pq] = ffma2r(acc1[pq], coefd, raw[pq]);
+            } else {
+#pragma unroll
+                for (int pq = 0; pq < NPAIR; pq++) raw[pq] = ffma2r(acc2[pq], coefd, raw[pq]);
+            }
             u64 Gi = 0ull;
             float Si = 0.f;
             if (HOOK) {   // parity hook only: the unclamped TAC
 #pragma unroll
                 for (int pq = 0; pq < NPAIR; pq++) {
                     float c0, c1;
-                    unpack2(PETMH_SEL(acc0[pq], acc1[pq], acc2[pq]), c0, c1);
-                    tac_out[it * NT + blk * RB + 2 * pq] = fmaf(coefi, c0, r1i * crb[2 * pq]);
-                    tac_out[it * NT + blk * RB + 2 * pq + 1] = fmaf(coefi, c1, r1i * crb[2 * pq + 1]);
+                    unpack2(raw[pq], c0, c1);
+                    tac_out[it * NT + blk * RB + 2 * pq] = c0;
+                    tac_out[it * NT + blk * RB + 2 * pq + 1] = c1;
                 }
             }
 #pragma unroll
@@ -410,34 +426,26 @@ __device__ __noinline__ float3 eval3(const int l16, const float d0, const float 
                 if (g < 4) {
                     const float4 cv = *reinterpret_cast<const float4*>(crow + 4 * g);
                     const float4 yv = *reinterpret_cast<const float4*>(yrow + 4 * g);
-                    const float2 ca = *reinterpret_cast<const float2*>(crb + 4 * g);
-                    const float2 cb = *reinterpret_cast<const float2*>(crb + 4 * g + 2);
-                    frame_pair(PETMH_SEL(acc0[2 * g], acc1[2 * g], acc2[2 * g]), pack2(ca.x, ca.y), pack2(cv.x, cv.y), pack2(yv.x, yv.y), coefd, r1d, Gi, sp[0], zp[0]);
-                    frame_pair(PETMH_SEL(acc0[2 * g + 1], acc1[2 * g + 1], acc2[2 * g + 1]), pack2(cb.x, cb.y), pack2(cv.z, cv.w), pack2(yv.z, yv.w), coefd, r1d, Gi, sp[1], zp[1]);
+                    frame_pair(raw[2 * g], pack2(cv.x, cv.y), pack2(yv.x, yv.y), Gi, sp[0], zp[0]);
+                    frame_pair(raw[2 * g + 1], pack2(cv.z, cv.w), pack2(yv.z, yv.w), Gi, sp[1], zp[1]);
                     Si += trunc_log2<2>(sp, zp);
                 } else {
                     const float2 cv = *reinterpret_cast<const float2*>(crow + 16);
                     const float2 yv = *reinterpret_cast<const float2*>(yrow + 16);
-                    const float2 ca = *reinterpret_cast<const float2*>(crb + 16);
-                    frame_pair(PETMH_SEL(acc0[8], acc1[8], acc2[8]), pack2(ca.x, ca.y), pack2(cv.x, cv.y), pack2(yv.x, yv.y), coefd, r1d, Gi, sp[0], zp[0]);
+                    frame_pair(raw[8], pack2(cv.x, cv.y), pack2(yv.x, yv.y), Gi, sp[0], zp[0]);
                     sp[1] = zp[1] = 0ull;
                     Si += trunc_log2<1>(sp, zp);
                 }
             }
-            if (it == 0) { G0 = fadd2(G0, Gi); S0 += Si; }
-            else if (it == 1) { G1 = fadd2(G1, Gi); S1 += Si; }
-            else { G2 = fadd2(G2, Gi); S2 += Si; }
-#undef PETMH_SEL
+            float ga, gb;
+            unpack2(Gi, ga, gb);
+            const float vi = fmaf(-0.34657359027997264f, Si, -(ga + gb));   // -(ln 2)/2 * log2(prod) - Gaussian term
+            v0 += it == 0 ? vi : 0.f;
+            v1 += it == 1 ? vi : 0.f;
+            v2 += it == 2 ? vi : 0.f;
         }
     }
     const unsigned char* bad = smem + SM_BAD;
-    float ga, gb;
-    unpack2(G0, ga, gb);
-    const float v0 = -(ga + gb) - 0.34657359027997264f * S0;   // -(ln 2)/2 * log2(prod)
-    unpack2(G1, ga, gb);
-    const float v1 = -(ga + gb) - 0.34657359027997264f * S1;
-    unpack2(G2, ga, gb);
-    const float v2 = -(ga + gb) - 0.34657359027997264f * S2;
     return make_float3(bad[l16] ? -INFINITY : v0, bad[l16 + 16] ? -INFINITY : v1, bad[l16 + 32] ? -INFINITY : v2);
 }
 
