@@ -265,25 +265,35 @@ __device__ __forceinline__ u64 trunc_factor2(const u64 zp) {
 // warp-uniformly when every lane has z >= Z_CUT; whether it applies to a given element depends
 // on that element's z alone (branch-free select), never on neighbouring lanes.
 template <int NP>
-__device__ __forceinline__ float trunc_log2(const u64 (&sp)[2], const u64 (&zp)[2]) {
-    float z0, z1, z2, z3;
-    unpack2(zp[0], z0, z1);
-    float zmin = fminf(z0, z1);
-    if (NP == 2) { unpack2(zp[1], z2, z3); zmin = fminf(zmin, fminf(z2, z3)); }
-    u64 prp = sp[0];
-    if (__any_sync(0xffffffffu, !(zmin >= Z_CUT))) {   // NaN -> evaluate
-        const u64 g0 = trunc_factor2(zp[0]);
-        prp = fmul2(fmul2(sp[0], g0), g0);
-        if (NP == 2) {
-            const u64 g1 = trunc_factor2(zp[1]);
-            prp = fmul2(prp, fmul2(fmul2(sp[1], g1), g1));
-        }
-    } else if (NP == 2) {
-        prp = fmul2(prp, sp[1]);
+__device__ __forceinline__ float trunc_log2(const u64 (&sp)[NP], const u64 (&zp)[NP]) {
+    float zmin = CUDART_INF_F;
+#pragma unroll
+    for (int k = 0; k < NP; k++) {
+        float z0, z1;
+        unpack2(zp[k], z0, z1);
+        zmin = fminf(zmin, fminf(z0, z1));
     }
-    float pa, pb;
-    unpack2(prp, pa, pb);
-    return lg2_approx(pa * pb);
+    u64 prp[NP];
+    if (__any_sync(0xffffffffu, !(zmin >= Z_CUT))) {   // NaN -> evaluate
+#pragma unroll
+        for (int k = 0; k < NP; k++) {
+            const u64 g = trunc_factor2(zp[k]);
+            prp[k] = fmul2(fmul2(sp[k], g), g);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < NP; k++) prp[k] = sp[k];
+    }
+    // one lg2 per two pairs (four frames): a longer product could leave the fp32 range for clamped TACs
+    float out = 0.f;
+#pragma unroll
+    for (int k = 0; k < NP; k += 2) {
+        const u64 pr = (k + 1 < NP) ? fmul2(prp[k], prp[k + 1]) : prp[k];
+        float pa, pb;
+        unpack2(pr, pa, pb);
+        out += lg2_approx(pa * pb);
+    }
+    return out;
 }
 
 // HOOK = true only in the parity-hook / generator kernels (writes the unclamped TAC to tac_out); the sweep kernel's
@@ -421,21 +431,23 @@ __device__ __noinline__ float3 eval3(const int l16, const float d0, const float 
                 }
             }
 #pragma unroll
-            for (int g = 0; g < 5; g++) {
-                u64 sp[2], zp[2];
-                if (g < 4) {
-                    const float4 cv = *reinterpret_cast<const float4*>(crow + 4 * g);
-                    const float4 yv = *reinterpret_cast<const float4*>(yrow + 4 * g);
-                    frame_pair(raw[2 * g], pack2(cv.x, cv.y), pack2(yv.x, yv.y), Gi, sp[0], zp[0]);
-                    frame_pair(raw[2 * g + 1], pack2(cv.z, cv.w), pack2(yv.z, yv.w), Gi, sp[1], zp[1]);
-                    Si += trunc_log2<2>(sp, zp);
-                } else {
-                    const float2 cv = *reinterpret_cast<const float2*>(crow + 16);
-                    const float2 yv = *reinterpret_cast<const float2*>(yrow + 16);
-                    frame_pair(raw[8], pack2(cv.x, cv.y), pack2(yv.x, yv.y), Gi, sp[0], zp[0]);
-                    sp[1] = zp[1] = 0ull;
-                    Si += trunc_log2<1>(sp, zp);
+            for (int g = 0; g < 2; g++) {   // frames 0..7, 8..15: four pairs per erfc vote
+                u64 sp[4], zp[4];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const float4 cv = *reinterpret_cast<const float4*>(crow + 8 * g + 4 * h);
+                    const float4 yv = *reinterpret_cast<const float4*>(yrow + 8 * g + 4 * h);
+                    frame_pair(raw[4 * g + 2 * h], pack2(cv.x, cv.y), pack2(yv.x, yv.y), Gi, sp[2 * h], zp[2 * h]);
+                    frame_pair(raw[4 * g + 2 * h + 1], pack2(cv.z, cv.w), pack2(yv.z, yv.w), Gi, sp[2 * h + 1], zp[2 * h + 1]);
                 }
+                Si += trunc_log2<4>(sp, zp);
+            }
+            {   // frames 16, 17
+                u64 sp[1], zp[1];
+                const float2 cv = *reinterpret_cast<const float2*>(crow + 16);
+                const float2 yv = *reinterpret_cast<const float2*>(yrow + 16);
+                frame_pair(raw[8], pack2(cv.x, cv.y), pack2(yv.x, yv.y), Gi, sp[0], zp[0]);
+                Si += trunc_log2<1>(sp, zp);
             }
             float ga, gb;
             unpack2(Gi, ga, gb);
