@@ -135,6 +135,11 @@ int petmh_get_summary(petmh_t* h, float* out);
 /* same, written to a DEVICE buffer (e.g. a slice of an NCCL all-gather buffer) on
  * `stream` (a cudaStream_t, 0 = the handle's). */
 int petmh_summary_device(petmh_t* h, float* d_out, void* stream);
+/* out[n_tac][96] f32: cross-chain effective sample size of every coordinate from the stored draws,
+ * as the consumer computes it with tfp.mcmc.effective_sample_size(..., cross_chain_dims=-1)
+ * (main_script.py:807-810; TFP defaults: lags from the first negative autocorrelation on dropped).
+ * Needs max_draws > 0 and >= 2 stored draws; one chain falls back to the single-chain formula. */
+int petmh_get_ess_cross_chain(petmh_t* h, float* out);
 int petmh_get_state(petmh_t* h, float* q /*[n_tac][n_chains][96]*/, float* scale /*same*/);
 /* Resume / warm start: overwrite every chain's position and scaling (either may be NULL),
  * zero the tuning counters and the running moments, and set the sweep counter. */

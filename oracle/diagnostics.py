@@ -130,3 +130,28 @@ def summary_row(a):
     """mean, sd, mcse_mean, ess_bulk, ess_tail, r_hat -- the GPU summary's first six columns."""
     a = np.asarray(a, np.float64)
     return np.array([a.mean(), a.std(ddof=1), mcse_mean(a), ess_bulk(a), ess_tail(a), rhat_rank(a)])
+
+
+def tfp_ess_cross_chain(a):
+    """tfp.mcmc.effective_sample_size(x, cross_chain_dims=...) with its defaults (filter_threshold=0.,
+    filter_beyond_lag=None, filter_beyond_positive_pairs=False) for one scalar quantity -- what the
+    consumer computes from DVR_mcmc / R1_mcmc (main_script.py:807-810).  a: (n_chain, n_draw).
+
+    PARITY UNPINNED (tensorflow_probability==0.24.0 is third-party and absent).  Restated from TFP's
+    published algorithm: per-chain auto-covariance with the unbiased 1/(N-k) normalisation
+    (tfp.stats.auto_correlation, normalize=False, center=True), W = mean biased within-chain variance,
+    B/N = unbiased variance of the chain means, rho_k = 1 - (W - mean_c acov_k) / (W + B/N), every lag from
+    the first rho_k < 0 on dropped, ESS = C N / (-1 + 2 sum_k (N-k)/N rho_k).  One chain: rho_k = acov_k/acov_0.
+    """
+    a = np.asarray(a, np.float64)
+    n_chain, n = a.shape
+    k = np.arange(n)
+    acov = np.stack([autocov(row) * n / (n - k) for row in a])          # (C, N), 1/(N-k) normalisation
+    if n_chain > 1:
+        w_biased = acov[:, 0].mean()
+        b_div_n = a.mean(axis=1).var(ddof=1)
+        rho = 1.0 - (w_biased - acov.mean(axis=0)) / (w_biased + b_div_n)
+    else:
+        rho = acov[0] / acov[0, 0]
+    mask = np.maximum(1.0 - np.cumsum(rho < 0.0), 0.0)
+    return n_chain * n / (-1.0 + 2.0 * np.sum((n - k) / n * rho * mask))

@@ -58,6 +58,7 @@ def _load():
         "petmh_get_chains": (C.c_int, [H, fp, fp]),
         "petmh_get_summary": (C.c_int, [H, fp]),
         "petmh_summary_device": (C.c_int, [H, C.c_void_p, C.c_void_p]),
+        "petmh_get_ess_cross_chain": (C.c_int, [H, fp]),
         "petmh_get_state": (C.c_int, [H, fp, fp]),
         "petmh_set_state": (C.c_int, [H, fp, fp, C.c_int]),
         "petmh_set_stream": (C.c_int, [H, C.c_void_p]),

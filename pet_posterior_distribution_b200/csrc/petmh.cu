@@ -777,6 +777,24 @@ extern "C" int petmh_get_summary(petmh_t* h, float* out) {
     return PETMH_OK;
 }
 
+extern "C" int petmh_get_ess_cross_chain(petmh_t* h, float* out) {
+    if (!h || !out) return fail(h, PETMH_EINVAL, "null argument");
+    int rc = check_ready(h);
+    if (rc) return rc;
+    const int n_stored = petmh_n_stored(h);
+    if (h->cfg.max_draws <= 0 || n_stored < 2)
+        return fail(h, PETMH_EINVAL, "cross-chain ESS needs stored draws (max_draws > 0, >= 2 draws stored; have %d)", n_stored);
+    CU(cudaSetDevice(h->cfg.device));
+    float* d_out = nullptr;
+    CU(cudaMallocAsync(&d_out, (size_t)h->n_tac * 96 * sizeof(float), h->stream));
+    const int e = launch_tfp_ess(h->d_draws, h->n_tac, h->cfg.n_chains, h->cfg.max_draws, n_stored, d_out, h->stream);
+    if (e) { cudaFreeAsync(d_out, h->stream); return fail(h, PETMH_ECUDA, "tfp_ess: %s", cudaGetErrorString((cudaError_t)e)); }
+    CU(cudaMemcpyAsync(out, d_out, (size_t)h->n_tac * 96 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaFreeAsync(d_out, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return PETMH_OK;
+}
+
 // ---- K4: synthetic data on the GPU ---------------------------------------------------------
 // pivoted Cholesky of a symmetric positive SEMI-definite matrix: cov ~= A A^T, A is n x rank
 // (numpy.random.multivariate_normal tolerates the rank-deficient Cov_tac_ref through an SVD; any

@@ -318,4 +318,102 @@ done:
     return (int)e;
 }
 
+// ---- TFP-style cross-chain ESS (consumer side: main_script.py:807-810) ----------------------
+// tfp.mcmc.effective_sample_size(x, cross_chain_dims) with its defaults, restated (PARITY UNPINNED:
+// tensorflow_probability is third-party and absent; checked against oracle/diagnostics.py
+// tfp_ess_cross_chain): unsplit chains, raw values, per-chain auto-covariance normalised by 1/(N-k),
+// rho_k = 1 - (W - mean_c acov_k) / (W + B/N), lags from the first rho_k < 0 on dropped,
+// ESS = C N / (-1 + 2 sum_k (N-k)/N rho_k).
+__global__ void tfp_gather(const float* draws, int n_chains, int max_draws, int n_stored, int tac0, float* xc, size_t n) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const size_t per_seg = (size_t)n_chains * n_stored;
+    const int seg = (int)(e / per_seg);
+    const size_t k = e - (size_t)seg * per_seg;
+    const int c = (int)(k / n_stored), d = (int)(k - (size_t)c * n_stored);
+    const int tac = tac0 + seg / 96, coord = seg % 96;
+    xc[e] = draws[(((size_t)tac * n_chains + c) * max_draws + d) * 96 + coord];
+}
+
+constexpr int TFP_LB = 256;   // lags per batch
+__global__ void __launch_bounds__(TFP_LB) tfp_ess(float* xc /*[nseg][C][N], centred in place*/, int C, int N, float* out) {
+    __shared__ double sh[32];
+    __shared__ int s_stop;
+    __shared__ double s_sum;
+    const int seg = blockIdx.x, tid = threadIdx.x;
+    float* x = xc + (size_t)seg * C * N;
+    double w_biased = 0.0, sm = 0.0, sm2 = 0.0;
+    for (int c = 0; c < C; c++) {
+        float* xr = x + (size_t)c * N;
+        double s = 0;
+        for (int i = tid; i < N; i += blockDim.x) s += xr[i];
+        const double mean = block_sum(s, sh) / N;
+        double q = 0;
+        for (int i = tid; i < N; i += blockDim.x) { const float d = (float)((double)xr[i] - mean); xr[i] = d; q += (double)d * d; }
+        w_biased += block_sum(q, sh) / N;
+        sm += mean; sm2 += mean * mean;
+    }
+    __syncthreads();
+    w_biased /= C;
+    const double b_div_n = C > 1 ? (sm2 - sm * sm / C) / (C - 1) : 0.0;
+    const double approx = w_biased + b_div_n;
+    if (!(w_biased > 0.0) || N < 2) {
+        if (tid == 0) out[seg] = CUDART_NAN_F;
+        return;
+    }
+    if (tid == 0) { s_stop = 0; s_sum = 0.0; }
+    __syncthreads();
+    for (int k0 = 0; k0 < N; k0 += TFP_LB) {
+        const int k = k0 + tid;
+        double rho = 0.0;
+        if (k < N) {
+            double acov = 0.0;
+            for (int c = 0; c < C; c++) {
+                const float* xr = x + (size_t)c * N;
+                double a = 0.0;
+                for (int n = 0; n + k < N; n++) a += (double)xr[n] * (double)xr[n + k];
+                acov += a / (N - k);
+            }
+            acov /= C;
+            rho = C > 1 ? 1.0 - (w_biased - acov) / approx : acov / w_biased;
+        }
+        // first negative lag of the batch (lags beyond N count as negative)
+        const unsigned neg = __ballot_sync(0xffffffffu, !(k < N) || rho < 0.0);
+        __shared__ int first_neg[TFP_LB / 32];
+        if ((tid & 31) == 0) first_neg[tid >> 5] = neg ? (tid + __ffs(neg) - 1) : TFP_LB;
+        __syncthreads();
+        int fn = TFP_LB;
+        for (int w = 0; w < TFP_LB / 32; w++) fn = min(fn, first_neg[w]);
+        const double term = tid < fn ? (double)(N - k) / N * rho : 0.0;
+        const double bs = block_sum(term, sh);
+        if (tid == 0) { s_sum += bs; if (fn < TFP_LB) s_stop = 1; }
+        __syncthreads();
+        if (s_stop) break;
+    }
+    if (tid == 0) out[seg] = (float)((double)C * N / (-1.0 + 2.0 * s_sum));
+}
+
+// Host driver: out[n_tac][96] (device).  Returns a cudaError_t (0 = ok).
+static inline int launch_tfp_ess(const float* d_draws, int n_tac_total, int n_chains, int max_draws, int n_stored,
+                                 float* d_out, cudaStream_t st) {
+    if (n_stored < 2) return (int)cudaErrorInvalidValue;
+    const size_t per_seg = (size_t)n_chains * n_stored;
+    const size_t max_elems = (size_t)1 << 28;
+    int tacs_per_batch = (int)std::max<size_t>(1, max_elems / ((size_t)96 * per_seg));
+    tacs_per_batch = std::min(tacs_per_batch, n_tac_total);
+    float* xc = nullptr;
+    cudaError_t e = cudaMallocAsync(&xc, (size_t)tacs_per_batch * 96 * per_seg * 4, st);
+    if (e != cudaSuccess) return (int)e;
+    for (int t0 = 0; t0 < n_tac_total; t0 += tacs_per_batch) {
+        const int nt = std::min(tacs_per_batch, n_tac_total - t0);
+        const size_t n = (size_t)nt * 96 * per_seg;
+        tfp_gather<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_draws, n_chains, max_draws, n_stored, t0, xc, n);
+        tfp_ess<<<nt * 96, TFP_LB, 0, st>>>(xc, n_chains, n_stored, d_out + (size_t)t0 * 96);
+    }
+    e = cudaGetLastError();
+    cudaFreeAsync(xc, st);
+    const cudaError_t e2 = cudaStreamSynchronize(st);
+    return (int)(e != cudaSuccess ? e : e2);
+}
+
 }  // namespace petmh

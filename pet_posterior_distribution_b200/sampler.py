@@ -211,6 +211,13 @@ class MHSampler:
         self._ck(_lib.lib.petmh_get_summary(self._h, _f(out)))
         return out
 
+    def ess_cross_chain(self):
+        """(S, 96) float32: tfp.mcmc.effective_sample_size(..., cross_chain_dims=-1) of the stored draws
+        (what main_script.py:807-810 computes from DVR_mcmc / R1_mcmc), on the GPU."""
+        out = np.empty((self.n_tac, N_COORD), np.float32)
+        self._ck(_lib.lib.petmh_get_ess_cross_chain(self._h, _f(out)))
+        return out
+
     def summary_into(self, device_ptr, stream=None):
         """Write the (S,96,8) f32 summary to DEVICE memory (e.g. an all-gather slot)."""
         self._ck(_lib.lib.petmh_summary_device(self._h, C.c_void_p(int(device_ptr)),

@@ -73,3 +73,33 @@ def test_many_chains_config4_shape(dataset, prior):
     assert np.isfinite(sm[:, :6]).all() and (sm[:, 3] > 100).all() and sm[:, 5].max() < 1.5
     dvr, _ = s.chains()
     assert dvr.shape == (1, 1024, 100, 48)
+
+
+def test_tfp_cross_chain_ess_matches_oracle(dataset, prior):
+    """petmh_get_ess_cross_chain vs the numpy restatement of tfp.mcmc.effective_sample_size(cross_chain_dims)."""
+    from oracle import diagnostics as dg
+    s = make_sampler(dataset, prior, n_chains=4, max_draws=1500, seed=9, tacs=[0, 3])
+    s.run(draws=1500, tune=1500)
+    dvr, r1 = s.chains()
+    ess = s.ess_cross_chain()
+    assert ess.shape == (2, 96) and np.isfinite(ess).all() and (ess > 1).all() and (ess <= 4 * 1500 * 1.0001).all()
+    worst = 0.0
+    for tac in range(2):
+        for coord in range(0, 96, 5):
+            a = (dvr if coord < 48 else r1)[tac, :, :, coord % 48].astype(np.float64)
+            ref = dg.tfp_ess_cross_chain(a)
+            worst = max(worst, abs(ess[tac, coord] / ref - 1))
+    print("worst rel err of cross-chain ESS:", worst)
+    assert worst < 2e-3
+    # one chain: single-chain formula
+    s1 = make_sampler(dataset, prior, n_chains=1, max_draws=800, seed=9, tacs=[0])
+    s1.run(draws=800, tune=1500)
+    d1, _ = s1.chains()
+    e1 = s1.ess_cross_chain()
+    ref = dg.tfp_ess_cross_chain(d1[0, :, :, 7].astype(np.float64))
+    assert abs(e1[0, 7] / ref - 1) < 2e-3
+    # no stored draws -> loud error
+    s0 = make_sampler(dataset, prior, n_chains=4, max_draws=0, seed=9, tacs=[0])
+    s0.run(draws=50, tune=100)
+    with pytest.raises(RuntimeError):
+        s0.ess_cross_chain()

@@ -59,3 +59,33 @@ def test_autocov_matches_direct_sum():
     xc = x - x.mean()
     for lag in (0, 1, 7, 100):
         assert abs(a[lag] - (xc[: x.size - lag] * xc[lag:]).sum() / x.size) < 1e-12
+
+
+def test_tfp_cross_chain_ess_ar1():
+    """TFP-style cross-chain ESS (main_script.py:807-810) on AR(1) chains: N C (1-phi)/(1+phi) within MC error;
+    single-chain fallback; lag truncation at the first negative autocorrelation (direct-sum check)."""
+    rng = np.random.default_rng(3)
+    for phi in (0.5, 0.9):
+        x = _ar1(rng, 4, 20000, phi)
+        got = dg.tfp_ess_cross_chain(x)
+        want = 4 * 20000 * (1 - phi) / (1 + phi)
+        assert abs(got / want - 1) < 0.08, (phi, got, want)
+        one = dg.tfp_ess_cross_chain(x[:1])
+        assert abs(one / (want / 4) - 1) < 0.15
+    # direct restatement with explicit loops on a short series
+    x = _ar1(rng, 3, 300, 0.7)
+    C, N = x.shape
+    xc = x - x.mean(axis=1, keepdims=True)
+    w = (xc ** 2).mean(axis=1).mean()
+    b = x.mean(axis=1).var(ddof=1)
+    tot = 0.0
+    for k in range(N):
+        acov = np.mean([np.dot(xc[c, :N - k], xc[c, k:]) / (N - k) for c in range(C)])
+        rho = 1 - (w - acov) / (w + b)
+        if rho < 0:
+            break
+        tot += (N - k) / N * rho
+    assert abs(dg.tfp_ess_cross_chain(x) / (C * N / (-1 + 2 * tot)) - 1) < 1e-10
+    # chains that disagree: between-chain variance inflates the autocorrelation -> much smaller ESS
+    y = x + np.arange(3)[:, None] * 5.0
+    assert dg.tfp_ess_cross_chain(y) < 0.1 * dg.tfp_ess_cross_chain(x)
