@@ -600,8 +600,8 @@ extern "C" int petmh_advance(petmh_t* h, int n_sweeps) {
         const int half = (drawing && h->sweep >= half_at) ? 1 : 0;
         p.mom_half = half;
         p.mom_n_before = h->mom_n[half];
-        if (h->variant == 0) mh_sweep_kernel<0, false><<<grid, nthr, smem_bytes(nthr), h->stream>>>(p);
-        else mh_sweep_kernel<1, false><<<grid, nthr, smem_bytes(nthr), h->stream>>>(p);
+        if (h->variant == 0) mh_sweep_kernel<0, false><<<grid, nthr, smem_bytes(256), h->stream>>>(p);
+        else mh_sweep_kernel<1, false><<<grid, nthr, smem_bytes(128), h->stream>>>(p);
         CU(cudaGetLastError());
         if (drawing) { h->mom_n[half] += n; h->mom_launches[half] += 1; }
         h->sweep += n;
@@ -656,7 +656,7 @@ extern "C" int petmh_run_taped(petmh_t* h, int tac, int n_tape_chains, int n_swe
         const int nthr = std::min(256, (n_tape_chains * 16 + 31) / 32 * 32);
         const int cpc = nthr / 16;
         const unsigned grid = (unsigned)((n_tape_chains + cpc - 1) / cpc);
-        mh_sweep_kernel<0, true><<<grid, nthr, smem_bytes(nthr), h->stream>>>(p);
+        mh_sweep_kernel<0, true><<<grid, nthr, smem_bytes(256), h->stream>>>(p);
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(draws_out, dd, n * 4, cudaMemcpyDeviceToHost, h->stream));
         if (delta_out) CU(cudaMemcpyAsync(delta_out, ddelta, n * 4, cudaMemcpyDeviceToHost, h->stream));

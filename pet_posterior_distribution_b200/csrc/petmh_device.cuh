@@ -583,9 +583,10 @@ __global__ void __launch_bounds__(VARIANT == 0 ? 256 : 128, VARIANT == 0 ? 2 : 3
 
     load_tac_image(p, tac, smem, tid, nthr);
     float* st = reinterpret_cast<float*>(smem + SM_STATE) + tid;
-#define ST_F(w) st[(w) * nthr]
-#define ST_I(w) reinterpret_cast<int*>(st)[(w) * nthr]
-#define ST_U(w) reinterpret_cast<unsigned*>(st)[(w) * nthr]
+    constexpr int ST_STRIDE = VARIANT == 0 ? 256 : 128;   // compile-time stride: every state word is [st + immediate]
+#define ST_F(w) st[(w) * ST_STRIDE]
+#define ST_I(w) reinterpret_cast<int*>(st)[(w) * ST_STRIDE]
+#define ST_U(w) reinterpret_cast<unsigned*>(st)[(w) * ST_STRIDE]
 
     // ---- load chain state; r = P (q - mu) in fp64 (q staged through shuffles) ----
     float ll_old[SLOTS];
@@ -662,9 +663,12 @@ __global__ void __launch_bounds__(VARIANT == 0 ? 256 : 128, VARIANT == 0 ? 2 : 3
                     logu[s] = active ? p.tape_logu[o] : 0.f;
                     key[s] = (((active ? (uint32_t)p.tape_rank[o] : (uint32_t)i) + 1u) << 6) | (uint32_t)i;
                 } else {
-                    const uint4 x = philox4x32_10(
-                        make_uint4((uint32_t)i, (uint32_t)(2 * sweep + b), (uint32_t)gid, (uint32_t)(gid >> 32)),
-                        make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+                    // (opaque copies: otherwise the loop-invariant first-round products of the coordinate and chain
+                    // words are hoisted out of the sweep loop and spilled -- reloading them costs more than 2 IMAD)
+                    uint32_t ci = (uint32_t)i, glo = (uint32_t)gid;
+                    asm volatile("" : "+r"(ci), "+r"(glo));
+                    const uint4 x = philox4x32_10(make_uint4(ci, (uint32_t)(2 * sweep + b), glo, (uint32_t)(gid >> 32)),
+                                                  make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
                     // Box-Muller (cos branch) with MUFU lg2 / sqrt / cos; ln u = lg2(u) * ln 2
                     nrm = sqrt_approx(-1.3862943611198906f * lg2_approx(u01(x.x))) * cos_approx(6.283185307179586f * u01(x.y));
                     logu[s] = 0.6931471805599453f * lg2_approx(u01(x.z));
