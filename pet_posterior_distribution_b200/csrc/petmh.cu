@@ -66,6 +66,7 @@ struct petmh_handle {
     int last_launches = 0;
     int launch_sweeps = 200;
     int variant = 0;
+    int wide = -1;                // -1 auto, 0 never, 1 always (PETMH_WIDE)
 };
 
 static int fail(petmh_t* h, int code, const char* fmt, ...) {
@@ -209,6 +210,7 @@ extern "C" int petmh_create(const petmh_cfg* cfg, petmh_t** out) {
     h->cfg = *cfg;
     if (const char* e = getenv("PETMH_LAUNCH_SWEEPS")) h->launch_sweeps = std::max(1, atoi(e));
     if (const char* e = getenv("PETMH_VARIANT")) h->variant = atoi(e) == 1 ? 1 : 0;
+    if (const char* e = getenv("PETMH_WIDE")) h->wide = atoi(e) ? 1 : 0;
     auto bail = [&](int code) { petmh_destroy(h); return code; };
 #define CUC(call)                                                                                     \
     do {                                                                                              \
@@ -252,6 +254,7 @@ extern "C" int petmh_create(const petmh_cfg* cfg, petmh_t** out) {
     CUC(cudaFuncSetAttribute(mh_sweep_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(256)));
     CUC(cudaFuncSetAttribute(mh_sweep_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(128)));
     CUC(cudaFuncSetAttribute(mh_sweep_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(256)));
+    CUC(cudaFuncSetAttribute(mh_sweep_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_wide()));
     CUC(cudaFuncSetAttribute(synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_STATE + 32 * SLOTS * NT * 4));
     CUC(cudaFuncSetAttribute(forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_STATE + 32 * SLOTS * NT * 4));
 #undef CUC
@@ -567,8 +570,16 @@ static int threads_per_cta(const petmh_t* h) {
     t = (t + 31) / 32 * 32;
     t = std::min(t, h->variant == 0 ? 256 : 128);
     // small jobs (e.g. one TAC x 64 chains): spread the chains over more, smaller CTAs so that every SM gets a
-    // warp -- the sweep loop is latency-bound per warp, and an under-filled GPU has SMs to spare
-    while (t > 32 && (size_t)h->n_tac * ((h->cfg.n_chains * 16 + t - 1) / t) < 2 * 148) t /= 2;
+    // warp -- the sweep loop is latency-bound per warp, and an under-filled GPU has SMs to spare.  CTA sizes stay
+    // whole warps: shrink through powers of two only (96 -> 64 -> 32, never 48).
+    auto groups = [&](int tt) { return (size_t)h->n_tac * ((h->cfg.n_chains * 16 + tt - 1) / tt); };
+    // ... and only while the smaller CTAs are still all resident at once (2 per SM): a second wave costs more
+    if (t > 32 && groups(t) < 2 * 148) {
+        int pw = 32;
+        while (pw * 2 <= t) pw *= 2;
+        if (groups(pw) <= 2 * 148) t = pw;
+        while (t > 32 && (t & (t - 1)) == 0 && groups(t / 2) <= 2 * 148) t /= 2;
+    }
     return t;
 }
 
@@ -578,8 +589,19 @@ extern "C" int petmh_advance(petmh_t* h, int n_sweeps) {
     if (n_sweeps < 0) return fail(h, PETMH_EINVAL, "n_sweeps < 0");
     if (!h->state_ready) return fail(h, PETMH_EINVAL, "chain state not initialised: call petmh_reset, petmh_run or petmh_set_state first");
     CU(cudaSetDevice(h->cfg.device));
-    const int nthr = threads_per_cta(h);
-    const int chains_per_cta = nthr / 16;
+    // small jobs: the wide kernel (three warps per chain pair) when even that leaves SMs to spare
+    const size_t pairs = (size_t)h->n_tac * ((h->cfg.n_chains + 1) / 2);
+    const bool wide = h->variant == 0 && (h->wide == 1 || (h->wide < 0 && pairs <= (size_t)WIDE_MAX_TRIPLES * 148));   // one wave
+    int nthr, chains_per_cta;
+    if (wide) {
+        int triples = 1;   // per CTA: one unless the CTAs would outnumber the SMs
+        while (triples < WIDE_MAX_TRIPLES && (size_t)h->n_tac * ((h->cfg.n_chains + 2 * triples - 1) / (2 * triples)) > 148) triples *= 2;
+        nthr = 96 * triples;
+        chains_per_cta = 2 * triples;
+    } else {
+        nthr = threads_per_cta(h);
+        chains_per_cta = nthr / 16;
+    }
     const int groups = (h->cfg.n_chains + chains_per_cta - 1) / chains_per_cta;
     const unsigned grid = (unsigned)((size_t)h->n_tac * groups);
     const int half_at = h->plan_tune + (h->plan_draws + 1) / 2;   // first sweep of the second half
@@ -600,7 +622,8 @@ extern "C" int petmh_advance(petmh_t* h, int n_sweeps) {
         const int half = (drawing && h->sweep >= half_at) ? 1 : 0;
         p.mom_half = half;
         p.mom_n_before = h->mom_n[half];
-        if (h->variant == 0) mh_sweep_kernel<0, false><<<grid, nthr, smem_bytes(256), h->stream>>>(p);
+        if (wide) mh_sweep_kernel<0, false, true><<<grid, nthr, smem_bytes_wide(), h->stream>>>(p);
+        else if (h->variant == 0) mh_sweep_kernel<0, false><<<grid, nthr, smem_bytes(256), h->stream>>>(p);
         else mh_sweep_kernel<1, false><<<grid, nthr, smem_bytes(128), h->stream>>>(p);
         CU(cudaGetLastError());
         if (drawing) { h->mom_n[half] += n; h->mom_launches[half] += 1; }

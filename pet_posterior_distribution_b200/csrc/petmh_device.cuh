@@ -461,6 +461,83 @@ __device__ __noinline__ float3 eval3(const int l16, const float d0, const float 
     return make_float3(bad[l16] ? -INFINITY : v0, bad[l16 + 16] ? -INFINITY : v1, bad[l16 + 32] ? -INFINITY : v2);
 }
 
+// One item per lane (the "wide" small-job path: the three ROI slots of a lane are evaluated by three warps).
+// Per item the operations and their order are exactly those of eval3, so the results are bit-identical.
+__device__ __noinline__ float eval1(const int roi, const float dv, const float av) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const float* sM = reinterpret_cast<const float*>(smem + SM_M);
+    const float* sCr = reinterpret_cast<const float*>(smem + SM_CR);
+    const float k2p = sCr[K2P_SLOT];
+    const float k2 = k2p * av, k2a = k2 / dv;
+    const float coef = fmaf(-av, k2a, k2);
+    const float na = k2a * -1.4426950408889634f;
+    const float* yrow0 = reinterpret_cast<const float*>(smem + SM_YCC) + roi * YS;
+    const float* crow0 = reinterpret_cast<const float*>(smem + SM_CC) + roi * YS;
+    const u64 coefd = pack2(coef, coef), r1d = pack2(av, av);
+    float v = 0.f;
+#pragma unroll 1
+    for (int blk = 0; blk < NBLK; blk++) {
+        const float4* Mp = reinterpret_cast<const float4*>(sM + (blk == 0 ? 0 : (blk == 1 ? 220 : 780)));   // PETMH_MOFF
+        u64 acc[NPAIR];
+#pragma unroll
+        for (int pq = 0; pq < NPAIR; pq++) acc[pq] = 0ull;
+#define PETMH_COL1(ZP)                                                                                           \
+    {                                                                                                            \
+        const float e_ = ex2_approx(na * c_tcol[c]);                                                             \
+        const u64 ed_ = pack2(e_, e_);                                                                           \
+        if ((ZP) <= 1) { const float4 m = Mp[0]; if ((ZP) <= 0) ffma2(acc[0], pack2(m.x, m.y), ed_); ffma2(acc[1], pack2(m.z, m.w), ed_); } \
+        if ((ZP) <= 3) { const float4 m = Mp[1]; if ((ZP) <= 2) ffma2(acc[2], pack2(m.x, m.y), ed_); ffma2(acc[3], pack2(m.z, m.w), ed_); } \
+        if ((ZP) <= 5) { const float4 m = Mp[2]; if ((ZP) <= 4) ffma2(acc[4], pack2(m.x, m.y), ed_); ffma2(acc[5], pack2(m.z, m.w), ed_); } \
+        if ((ZP) <= 7) { const float4 m = Mp[3]; if ((ZP) <= 6) ffma2(acc[6], pack2(m.x, m.y), ed_); ffma2(acc[7], pack2(m.z, m.w), ed_); } \
+        { const float2 m = *reinterpret_cast<const float2*>(Mp + 4); ffma2(acc[8], pack2(m.x, m.y), ed_); }       \
+    }
+#define PETMH_PHASE1(ZP, UNR)                                                                                    \
+    {                                                                                                            \
+        const int ce_ = c_cend[blk][ZP];                                                                          \
+        _Pragma(UNR) for (int c = (ZP) == 0 ? 0 : c_cend[blk][(ZP) == 0 ? 0 : (ZP) - 1]; c < ce_; c++, Mp += RSTRIDE / 4) PETMH_COL1(ZP) \
+    }
+        PETMH_PHASE1(0, "unroll 4")
+        PETMH_PHASE1(1, "unroll 1") PETMH_PHASE1(2, "unroll 1") PETMH_PHASE1(3, "unroll 1") PETMH_PHASE1(4, "unroll 1")
+        PETMH_PHASE1(5, "unroll 1") PETMH_PHASE1(6, "unroll 1") PETMH_PHASE1(7, "unroll 1") PETMH_PHASE1(8, "unroll 1")
+#undef PETMH_PHASE1
+#undef PETMH_COL1
+        const float* crb = sCr + blk * RB;
+        const float* yrow = yrow0 + blk * RSTRIDE;
+        const float* crow = crow0 + blk * RSTRIDE;
+        u64 raw[NPAIR];
+#pragma unroll
+        for (int pq = 0; pq < NPAIR; pq++) {
+            const float2 c = *reinterpret_cast<const float2*>(crb + 2 * pq);
+            raw[pq] = ffma2r(acc[pq], coefd, fmul2(pack2(c.x, c.y), r1d));
+        }
+        u64 Gi = 0ull;
+        float Si = 0.f;
+#pragma unroll
+        for (int g = 0; g < 2; g++) {
+            u64 sp[4], zp[4];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const float4 cv = *reinterpret_cast<const float4*>(crow + 8 * g + 4 * h);
+                const float4 yv = *reinterpret_cast<const float4*>(yrow + 8 * g + 4 * h);
+                frame_pair(raw[4 * g + 2 * h], pack2(cv.x, cv.y), pack2(yv.x, yv.y), Gi, sp[2 * h], zp[2 * h]);
+                frame_pair(raw[4 * g + 2 * h + 1], pack2(cv.z, cv.w), pack2(yv.z, yv.w), Gi, sp[2 * h + 1], zp[2 * h + 1]);
+            }
+            Si += trunc_log2<4>(sp, zp);
+        }
+        {
+            u64 sp[1], zp[1];
+            const float2 cv = *reinterpret_cast<const float2*>(crow + 16);
+            const float2 yv = *reinterpret_cast<const float2*>(yrow + 16);
+            frame_pair(raw[8], pack2(cv.x, cv.y), pack2(yv.x, yv.y), Gi, sp[0], zp[0]);
+            Si += trunc_log2<1>(sp, zp);
+        }
+        float ga, gb;
+        unpack2(Gi, ga, gb);
+        v += fmaf(-0.34657359027997264f, Si, -(ga + gb));
+    }
+    return (smem + SM_BAD)[roi] ? -INFINITY : v;
+}
+
 // ------------------------------------------------------------------------------------
 // Prologue helpers: build the per-TAC shared-memory image.
 // ------------------------------------------------------------------------------------
@@ -565,13 +642,28 @@ constexpr int ST_BLOCK = 18, ST_WORDS = 36;
 __host__ __device__ constexpr int smem_bytes(int nthreads) { return SM_STATE + ST_WORDS * 4 * nthreads; }
 
 // VARIANT 0: 256-thread CTAs, 2 CTAs/SM (128-register cap); VARIANT 1: 128-thread CTAs, 3 CTAs/SM (168).
-template <int VARIANT, bool TAPED>
-__global__ void __launch_bounds__(VARIANT == 0 ? 256 : 128, VARIANT == 0 ? 2 : 3) mh_sweep_kernel(const SweepParams p) {
+// WIDE (small jobs, e.g. one TAC x 64 chains, where a warp's latency and not the GPU's throughput sets the time):
+// warps come in triples; the leader warp (role 0) runs the sweep loop for its two chains exactly as in the normal
+// kernel, but the log-likelihood of ROI slot s is evaluated by the triple's warp s (eval1) -- arguments and results
+// cross through a small shared-memory mailbox and one named barrier per triple.  Same arithmetic per item, same
+// random numbers: the chains are bit-identical to the normal path's.
+constexpr int WIDE_MAX_TRIPLES = 4;
+constexpr int XCH_WORDS = 9;   // d[3], a[3], ll[3] per lane
+__device__ __forceinline__ void triple_barrier(int triple) {
+    asm volatile("bar.sync %0, 96;" ::"r"(1 + triple) : "memory");
+}
+__host__ __device__ constexpr int smem_bytes_wide() { return smem_bytes(256) + WIDE_MAX_TRIPLES * XCH_WORDS * 32 * 4; }
+
+template <int VARIANT, bool TAPED, bool WIDE = false>
+__global__ void __launch_bounds__(WIDE ? 96 * WIDE_MAX_TRIPLES : (VARIANT == 0 ? 256 : 128), WIDE ? 1 : (VARIANT == 0 ? 2 : 3))
+    mh_sweep_kernel(const SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5;
+    const int lane = tid & 31;
+    const int triple = WIDE ? (tid >> 5) / 3 : 0, role = WIDE ? (tid >> 5) % 3 : 0;
+    const int warp = WIDE ? triple : (tid >> 5);   // index of the chain pair within the CTA
     const int half = lane >> 4, l16 = lane & 15;
-    const int chains_per_cta = nthr >> 4;
+    const int chains_per_cta = WIDE ? (nthr / 96) * 2 : (nthr >> 4);
     const int groups_per_tac = (p.n_chains + chains_per_cta - 1) / chains_per_cta;
     const int tac = TAPED ? p.tape_tac : (int)(blockIdx.x / groups_per_tac);
     const int grp = TAPED ? (int)blockIdx.x : (int)(blockIdx.x % groups_per_tac);
@@ -580,9 +672,33 @@ __global__ void __launch_bounds__(VARIANT == 0 ? 256 : 128, VARIANT == 0 ? 2 : 3
     const size_t cg = (size_t)tac * p.n_chains + (active ? chain : 0);   // local chain index (state arrays)
     const unsigned long long gid = (p.tac_gid0 + (unsigned long long)tac) * (unsigned long long)p.n_chains +
                                    (unsigned long long)(active ? chain : 0);
+    float* xch = reinterpret_cast<float*>(smem + smem_bytes(256)) + triple * XCH_WORDS * 32 + lane;   // WIDE mailbox
 
     load_tac_image(p, tac, smem, tid, nthr);
-    float* st = reinterpret_cast<float*>(smem + SM_STATE) + tid;
+    if (WIDE && role != 0) {   // helper warp: evaluate slot `role` for the leader, once per eval site visit
+        const int n_eval = 1 + 2 * p.n_sweeps;
+#pragma unroll 1
+        for (int n = 0; n < n_eval; n++) {
+            triple_barrier(triple);
+            const float ll = eval1(l16 + 16 * role, xch[role * 32], xch[(3 + role) * 32]);
+            xch[(6 + role) * 32] = ll;
+            triple_barrier(triple);
+        }
+        return;
+    }
+    // leader-side evaluation of the three slots
+    auto eval_slots = [&](float d0, float d1, float d2, float a0, float a1, float a2) -> float3 {
+        if (WIDE) {
+            xch[0 * 32] = d0; xch[1 * 32] = d1; xch[2 * 32] = d2;
+            xch[3 * 32] = a0; xch[4 * 32] = a1; xch[5 * 32] = a2;
+            triple_barrier(triple);
+            const float v0 = eval1(l16, d0, a0);
+            triple_barrier(triple);
+            return make_float3(v0, xch[7 * 32], xch[8 * 32]);
+        }
+        return eval3<VARIANT>(l16, d0, d1, d2, a0, a1, a2, nullptr);
+    };
+    float* st = reinterpret_cast<float*>(smem + SM_STATE) + (WIDE ? triple * 32 + lane : tid);
     constexpr int ST_STRIDE = VARIANT == 0 ? 256 : 128;   // compile-time stride: every state word is [st + immediate]
 #define ST_F(w) st[(w) * ST_STRIDE]
 #define ST_I(w) reinterpret_cast<int*>(st)[(w) * ST_STRIDE]
@@ -631,7 +747,7 @@ __global__ void __launch_bounds__(VARIANT == 0 ? 256 : 128, VARIANT == 0 ? 2 : 3
             ST_F(b * ST_BLOCK + 14) = __int_as_float(__double2loint(r1)); ST_F(b * ST_BLOCK + 15) = __int_as_float(__double2hiint(r1));
             ST_F(b * ST_BLOCK + 16) = __int_as_float(__double2loint(r2)); ST_F(b * ST_BLOCK + 17) = __int_as_float(__double2hiint(r2));
         }
-        const float3 v = eval3<VARIANT>(l16, q0[0][0], q0[0][1], q0[0][2], q0[1][0], q0[1][1], q0[1][2], nullptr);
+        const float3 v = eval_slots(q0[0][0], q0[0][1], q0[0][2], q0[1][0], q0[1][1], q0[1][2]);
         ll_old[0] = v.x; ll_old[1] = v.y; ll_old[2] = v.z;
     }
     bool have_prev = false;
@@ -681,8 +797,8 @@ __global__ void __launch_bounds__(VARIANT == 0 ? 256 : 128, VARIANT == 0 ? 2 : 3
             float ll_new[SLOTS];
             {
                 const float o0 = ST_F(so + 0), o1 = ST_F(so + 1), o2 = ST_F(so + 2);
-                const float3 v = eval3<VARIANT>(l16, b ? o0 : qn[0], b ? o1 : qn[1], b ? o2 : qn[2],
-                                                b ? qn[0] : o0, b ? qn[1] : o1, b ? qn[2] : o2, nullptr);
+                const float3 v = eval_slots(b ? o0 : qn[0], b ? o1 : qn[1], b ? o2 : qn[2],
+                                            b ? qn[0] : o0, b ? qn[1] : o1, b ? qn[2] : o2);
                 ll_new[0] = v.x; ll_new[1] = v.y; ll_new[2] = v.z;
             }
             // ---- phase B: resolve visits in key order ----

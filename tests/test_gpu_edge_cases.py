@@ -8,18 +8,27 @@ from conftest import make_sampler
 pytestmark = pytest.mark.gpu
 
 
-def test_chain_streams_do_not_depend_on_chain_count(dataset, prior):
+def test_chain_streams_do_not_depend_on_chain_count(dataset, prior, monkeypatch):
     """Chain c of TAC 0 has Philox gid c whatever n_chains is: its draws are identical for
-    n_chains = 1, 3, 4 (different CTA shapes, idle half-warps) -> the thread mapping is invisible."""
-    runs = {}
-    for C in (1, 3, 4):
-        s = make_sampler(dataset, prior, n_chains=C, max_draws=30, seed=5, tacs=[0])
-        s.run(draws=30, tune=100)
-        runs[C] = s.chains()
-        assert runs[C][0].shape == (1, C, 30, 48) and np.isfinite(runs[C][0]).all()
-    assert np.array_equal(runs[1][0][0, 0], runs[4][0][0, 0]) and np.array_equal(runs[1][1][0, 0], runs[4][1][0, 0])
-    assert np.array_equal(runs[3][0][0, 2], runs[4][0][0, 2])
-    assert not np.array_equal(runs[4][0][0, 0], runs[4][0][0, 1])
+    n_chains = 1, 3, 4, 5, 6, 10, 12 (different CTA shapes, idle half-warps; 5/6/10/12 chains need 96/160/192
+    threads, which the small-job CTA shrink must not halve to a fraction of a warp) -> the thread mapping is
+    invisible.  Checked for the normal kernel (PETMH_WIDE=0) and for the automatic choice."""
+    for wide in ("0", None):
+        if wide is None:
+            monkeypatch.delenv("PETMH_WIDE", raising=False)
+        else:
+            monkeypatch.setenv("PETMH_WIDE", wide)
+        runs = {}
+        for C in (1, 3, 4, 5, 6, 10, 12):
+            s = make_sampler(dataset, prior, n_chains=C, max_draws=30, seed=5, tacs=[0])
+            s.run(draws=30, tune=100)
+            runs[C] = s.chains()
+            s.close()
+            assert runs[C][0].shape == (1, C, 30, 48) and np.isfinite(runs[C][0]).all()
+        ref = runs[12]
+        for C in (1, 3, 4, 5, 6, 10):
+            assert np.array_equal(runs[C][0][0], ref[0][0, :C]) and np.array_equal(runs[C][1][0], ref[1][0, :C]), C
+        assert not np.array_equal(ref[0][0, 0], ref[0][0, 1])
 
 
 def test_thinning_and_capacity(dataset, prior):
@@ -134,3 +143,22 @@ def test_large_batch_shard_invariance_and_determinism(dataset, prior):
     assert np.array_equal(np.concatenate([a, b]), full, equal_nan=True)
     # identical data, different global TAC index -> different Philox streams -> different chains
     assert not np.array_equal(full[0], full[k])
+
+
+def test_wide_small_job_path_is_bit_identical(dataset, prior, monkeypatch):
+    """Small jobs run the wide kernel (three warps per chain pair, one ROI slot each; petmh_device.cuh WIDE):
+    same random numbers, same per-item arithmetic -> chains, summaries and resumed state equal the normal
+    kernel's bit for bit.  Covers a ragged chain count (odd: half of the last pair idles) and CTAs of 1..4 triples."""
+    for n_chains, tacs in [(5, [0, 1]), (64, [2]), (16, list(range(24))), (32, list(range(20)))]:
+        out = {}
+        for wide in ("0", "1"):
+            monkeypatch.setenv("PETMH_WIDE", wide)
+            s = make_sampler(dataset, prior, n_chains=n_chains, max_draws=40, seed=11, tacs=[t % 4 for t in tacs])
+            s.run(draws=40, tune=230)            # crosses two tuning boundaries and the 200-sweep launch chunk
+            dvr, r1 = s.chains()
+            q, sc = s.state()
+            out[wide] = (dvr.copy(), r1.copy(), q.copy(), sc.copy(), s.summary().copy())
+            s.close()
+        for a, b in zip(out["0"], out["1"]):
+            assert np.array_equal(a, b, equal_nan=True)
+        assert np.isfinite(out["1"][0]).all()
