@@ -133,7 +133,7 @@ __global__ void rd_rhat(const float* z, const float* zf, int m, int h, float* rh
 }
 
 // arviz _ess for one (segment, series type); blockDim.x = ESS_LB lags per batch
-constexpr int ESS_LB = 256;
+constexpr int ESS_LB = 256, ESS_LAGS = 64;
 __global__ void __launch_bounds__(ESS_LB) rd_ess(const float* xs, const float* z, const float* q05, const float* q95, int m,
                                                  int h, float* rho_scratch /*[nseg*4][h]*/, float* ess_out /*[nseg][4]*/) {
     __shared__ double sh[32];
@@ -169,12 +169,15 @@ __global__ void __launch_bounds__(ESS_LB) rd_ess(const float* xs, const float* z
     __syncthreads();
     int have = 0;   // lags [1, have] available in rho as raw "1 - (mean_var - acov)/var_plus"
     int max_t = -1;
+    // a batch = ESS_LAGS lags x ESS_LB / ESS_LAGS chain groups (the Geyer cut-off is usually well inside the first batch)
+    __shared__ double part[ESS_LB];
+    const int tl = tid % ESS_LAGS, grp = tid / ESS_LAGS;
     while (true) {
-        // compute lags have+1 .. have+ESS_LB
-        const int t = have + 1 + tid;
+        // compute lags have+1 .. have+ESS_LAGS
+        const int t = have + 1 + tl;
         double acc = 0.0;
         if (t < h) {
-            for (int c = 0; c < m; c++) {
+            for (int c = grp; c < m; c += ESS_LB / ESS_LAGS) {
                 const double mu = cmean[min(c, 2047)];
                 const size_t o = base + (size_t)c * h;
                 double a = 0.0;
@@ -182,10 +185,15 @@ __global__ void __launch_bounds__(ESS_LB) rd_ess(const float* xs, const float* z
                     a += (series(ty, xs, z, a05, a95, o + n) - mu) * (series(ty, xs, z, a05, a95, o + n + t) - mu);
                 acc += a / h;
             }
+        }
+        part[tid] = acc;
+        __syncthreads();
+        if (grp == 0 && t < h) {
+            for (int g2 = 1; g2 < ESS_LB / ESS_LAGS; g2++) acc += part[g2 * ESS_LAGS + tl];
             rho[t] = (float)(1.0 - (mean_var - acc / m) / var_plus);
         }
         __syncthreads();
-        have = min(have + ESS_LB, h - 1);
+        have = min(have + ESS_LAGS, h - 1);
         if (tid == 0) {
             // Geyer's initial positive sequence, resumed where it stopped
             int tt = s_t;
