@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpetmh.so")
+LIB_PATH = os.environ.get("PETMH_LIB") or os.path.join(_HERE, "libpetmh.so")   # (PETMH_LIB: kernel-variant probes, tools/variant_probe.sh)
 
 N_ROI, N_FRAMES, N_COORD, N_STATS = 48, 54, 96, 8
 STAT_NAMES = ("mean", "sd", "mcse_mean", "ess_bulk", "ess_tail", "r_hat", "accept_rate", "scaling")

@@ -203,7 +203,9 @@ constexpr int SM_YCC = SM_CR + 64 * 4;                    // float [48][YS]  -(y
 constexpr int SM_CC = SM_YCC + 48 * YS * 4;               // float [48][YS]  1/(sigma sqrt2)
 constexpr int SM_BAD = SM_CC + 48 * YS * 4;               // uchar [48] (+pad) 1 if any y < 0
 constexpr int SM_P = SM_BAD + 64;                         // double [2][48][48] prior precision matrices
-constexpr int SM_STATE = SM_P + 2 * 48 * 48 * 8;          // float [ST_WORDS][nthreads] per-thread chain state
+constexpr int DM_STRIDE = 64;                             // doubles per chain (48 used; index 63 = "no winner" stays in range)
+constexpr int SM_DMOVE = SM_P + 2 * 48 * 48 * 8;          // double [8 warps][2 chains][DM_STRIDE] proposed moves of the block being resolved
+constexpr int SM_STATE = SM_DMOVE + 8 * 2 * DM_STRIDE * 8;// float [ST_WORDS][nthreads] per-thread chain state
 constexpr int K2P_SLOT = 60;
 
 // ------------------------------------------------------------------------------------
@@ -215,6 +217,12 @@ constexpr int K2P_SLOT = 60;
 // is only non-null in the parity hook.
 // ------------------------------------------------------------------------------------
 constexpr int K = SLOTS;
+// eval3 is inlined into its callers: as a real call, every value the sweep loop keeps live across it is spilled by the
+// ABI (232-byte frames x 512 threads thrash the ~30 KB of L1 left beside the shared memory: local loads hit 27 %);
+// inlined, the frame is 96 bytes and the kernel 4 % faster.  The second copy (initial log-likelihood) is cold code.
+#ifndef PETMH_EVAL3_INLINE
+#define PETMH_EVAL3_INLINE __forceinline__
+#endif
 #ifndef PETMH_TRIANGLE
 #define PETMH_TRIANGLE 1   // triangle-aware column phases: +2 % measured once the rest of the kernel got leaner
 #endif
@@ -265,7 +273,7 @@ __device__ __forceinline__ u64 trunc_factor2(const u64 zp) {
 // warp-uniformly when every lane has z >= Z_CUT; whether it applies to a given element depends
 // on that element's z alone (branch-free select), never on neighbouring lanes.
 template <int NP>
-__device__ __forceinline__ float trunc_log2(const u64 (&sp)[NP], const u64 (&zp)[NP]) {
+__device__ __forceinline__ float trunc_log2(const u64* __restrict__ sp, const u64* __restrict__ zp) {
     float zmin = CUDART_INF_F;
 #pragma unroll
     for (int k = 0; k < NP; k++) {
@@ -299,7 +307,7 @@ __device__ __forceinline__ float trunc_log2(const u64 (&sp)[NP], const u64 (&zp)
 // HOOK = true only in the parity-hook / generator kernels (writes the unclamped TAC to tac_out); the sweep kernel's
 // instance carries no hook code (hot-code size matters: the kernel is sensitive to instruction-cache misses).
 template <int VARIANT, bool HOOK = false>
-__device__ __noinline__ float3 eval3(const int l16, const float d0, const float d1, const float d2, const float a0,
+__device__ PETMH_EVAL3_INLINE float3 eval3(const int l16, const float d0, const float d1, const float d2, const float a0,
                                      const float a1, const float a2, float* tac_out) {
     extern __shared__ __align__(16) unsigned char smem[];
     const float* sM = reinterpret_cast<const float*>(smem + SM_M);
@@ -818,8 +826,13 @@ __global__ void __launch_bounds__(WIDE ? 96 * WIDE_MAX_TRIPLES : (VARIANT == 0 ?
                     key[s] = 0u;                                      // never opens
                 }
             }
+            // the block's moves, by coordinate, where every lane of the chain can read the winner's (one broadcast
+            // LDS.64 per round instead of a three-way select and two shuffles)
+            double* dmv = reinterpret_cast<double*>(smem + SM_DMOVE) + (warp * 2 + half) * DM_STRIDE;
+#pragma unroll
+            for (int s = 0; s < SLOTS; s++) dmv[s * 16 + l16] = d[s];
+            __syncwarp();
             uint32_t last = 0u;                                       // keys <= last are decided
-            int acc_mask = 0;
 #pragma unroll 1
             while (true) {
                 uint32_t cand = 0xffffffffu;
@@ -843,13 +856,7 @@ __global__ void __launch_bounds__(WIDE ? 96 * WIDE_MAX_TRIPLES : (VARIANT == 0 ?
                 if ((w_lo & w_hi) == 0xffffffffu) break;              // warp-uniform: both chains are done
                 const bool any_win = win != 0xffffffffu;
                 const int wi = (int)(win & 63u);                      // winning coordinate (63 if none)
-                const int ws = wi >> 4;
-                // branch-free select of the winner slot's move (both 32-bit halves), then broadcast
-                int dlo = __double2loint(d[0]), dhi = __double2hiint(d[0]);
-                dlo = ws == 1 ? __double2loint(d[1]) : dlo; dhi = ws == 1 ? __double2hiint(d[1]) : dhi;
-                dlo = ws == 2 ? __double2loint(d[2]) : dlo; dhi = ws == 2 ? __double2hiint(d[2]) : dhi;
-                const int src = (half << 4) | (wi & 15);
-                const double dw = __hiloint2double(__shfl_sync(0xffffffffu, dhi, src), __shfl_sync(0xffffffffu, dlo, src));
+                const double dw = dmv[wi];                            // the winner's move (unused garbage if none)
                 if (any_win) {
                     const double* Pc = Pl + wi * 48;
                     r[0] = fma(Pc[0], dw, r[0]);
@@ -857,14 +864,15 @@ __global__ void __launch_bounds__(WIDE ? 96 * WIDE_MAX_TRIPLES : (VARIANT == 0 ?
                     r[2] = fma(Pc[32], dw, r[2]);
 #pragma unroll
                     for (int s = 0; s < SLOTS; s++)
-                        if (key[s] == win) acc_mask |= 1 << s;
+                        if (key[s] == win) key[s] = 1u;               // accepted (1 < every live key; 0 = never opened)
                 }
                 last = any_win ? win : 0xfffffffeu;                   // a finished chain idles
             }
+            __syncwarp();                                             // dmv is rewritten by the next block
             // ---- commit the block ----
 #pragma unroll
             for (int s = 0; s < SLOTS; s++) {
-                if (acc_mask & (1 << s)) {
+                if (key[s] == 1u) {
                     ST_F(sb + s) = qn[s];
                     ll_old[s] = ll_new[s];
                     ST_I(sb + 6 + s) = ST_I(sb + 6 + s) + 1;
@@ -882,22 +890,28 @@ __global__ void __launch_bounds__(WIDE ? 96 * WIDE_MAX_TRIPLES : (VARIANT == 0 ?
                     ST_F((c / SLOTS) * ST_BLOCK + (c % SLOTS));
         }
         if (!tuning) {
-            const int di = sweep - p.tune_until;
-            const bool store = !TAPED && p.draws != nullptr && active && (di % p.thin) == 0 && (di / p.thin) < p.max_draws;
             if (!TAPED && active) {
+                // one base address per array and one (uniform, unsigned) division per sweep; the six coordinates
+                // of the lane sit at compile-time offsets from the bases
+                const unsigned di = (unsigned)(sweep - p.tune_until), dslot = di / (unsigned)p.thin;
+                const bool store = p.draws != nullptr && dslot * (unsigned)p.thin == di && dslot < (unsigned)p.max_draws;
+                const size_t o0 = cg * 96 + l16;
+                const float* qref = p.q + o0;                         // ref = q at launch start (p.q is rewritten in the epilogue only)
+                float4* mw = p.momw + o0;
+                float* dst = p.draws + (cg * p.max_draws + dslot) * 96 + l16;   // (only dereferenced if store)
 #pragma unroll
                 for (int c = 0; c < 2 * SLOTS; c++) {
-                    const size_t o = cg * 96 + (c / SLOTS) * 48 + (c % SLOTS) * 16 + l16;
+                    const int off = (c / SLOTS) * 48 + (c % SLOTS) * 16;
                     const float qv = ST_F((c / SLOTS) * ST_BLOCK + (c % SLOTS));
-                    const float x = qv - p.q[o];                      // ref = q at launch start (p.q is rewritten in the epilogue only)
-                    float4 m = p.momw[o];
+                    const float x = qv - qref[off];
+                    float4 m = mw[off];
                     m.x += x;
                     m.y = fmaf(x, x, m.y);
                     if (have_prev) m.z = fmaf(x, m.w, m.z);
-                    else p.mom_first[o] = x;                          // first draw of this launch
+                    else p.mom_first[o0 + off] = x;                   // first draw of this launch
                     m.w = x;
-                    p.momw[o] = m;
-                    if (store) p.draws[(cg * p.max_draws + di / p.thin) * 96 + (c / SLOTS) * 48 + (c % SLOTS) * 16 + l16] = qv;
+                    mw[off] = m;
+                    if (store) dst[off] = qv;
                 }
             }
             have_prev = true;
