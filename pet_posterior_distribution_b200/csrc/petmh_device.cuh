@@ -304,6 +304,36 @@ __device__ __forceinline__ float trunc_log2(const u64* __restrict__ sp, const u6
     return out;
 }
 
+// Log-likelihood (reduced, natural log) of one item's 18 frames of a row block from its unclamped TAC pairs.
+// One routine for eval3 and eval1: the operations and their order per item are the same on every path.
+__device__ __forceinline__ float block_loglik(const u64 (&raw)[NPAIR], const float* __restrict__ crow,
+                                              const float* __restrict__ yrow) {
+    u64 Gi = 0ull;
+    float Si = 0.f;
+#pragma unroll
+    for (int g = 0; g < 2; g++) {   // frames 0..7, 8..15: four pairs per erfc vote
+        u64 sp[4], zp[4];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const float4 cv = *reinterpret_cast<const float4*>(crow + 8 * g + 4 * h);
+            const float4 yv = *reinterpret_cast<const float4*>(yrow + 8 * g + 4 * h);
+            frame_pair(raw[4 * g + 2 * h], pack2(cv.x, cv.y), pack2(yv.x, yv.y), Gi, sp[2 * h], zp[2 * h]);
+            frame_pair(raw[4 * g + 2 * h + 1], pack2(cv.z, cv.w), pack2(yv.z, yv.w), Gi, sp[2 * h + 1], zp[2 * h + 1]);
+        }
+        Si += trunc_log2<4>(sp, zp);
+    }
+    {   // frames 16, 17
+        u64 sp[1], zp[1];
+        const float2 cv = *reinterpret_cast<const float2*>(crow + 16);
+        const float2 yv = *reinterpret_cast<const float2*>(yrow + 16);
+        frame_pair(raw[8], pack2(cv.x, cv.y), pack2(yv.x, yv.y), Gi, sp[0], zp[0]);
+        Si += trunc_log2<1>(sp, zp);
+    }
+    float ga, gb;
+    unpack2(Gi, ga, gb);
+    return fmaf(-0.34657359027997264f, Si, -(ga + gb));   // -(ln 2)/2 * log2(prod) - Gaussian term
+}
+
 // HOOK = true only in the parity-hook / generator kernels (writes the unclamped TAC to tac_out); the sweep kernel's
 // instance carries no hook code (hot-code size matters: the kernel is sensitive to instruction-cache misses).
 template <int VARIANT, bool HOOK = false>
@@ -427,8 +457,6 @@ __device__ PETMH_EVAL3_INLINE float3 eval3(const int l16, const float d0, const 
 #pragma unroll
                 for (int pq = 0; pq < NPAIR; pq++) raw[pq] = ffma2r(acc2[pq], coefd, raw[pq]);
             }
-            u64 Gi = 0ull;
-            float Si = 0.f;
             if (HOOK) {   // parity hook only: the unclamped TAC
 #pragma unroll
                 for (int pq = 0; pq < NPAIR; pq++) {
@@ -438,28 +466,7 @@ __device__ PETMH_EVAL3_INLINE float3 eval3(const int l16, const float d0, const 
                     tac_out[it * NT + blk * RB + 2 * pq + 1] = c1;
                 }
             }
-#pragma unroll
-            for (int g = 0; g < 2; g++) {   // frames 0..7, 8..15: four pairs per erfc vote
-                u64 sp[4], zp[4];
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const float4 cv = *reinterpret_cast<const float4*>(crow + 8 * g + 4 * h);
-                    const float4 yv = *reinterpret_cast<const float4*>(yrow + 8 * g + 4 * h);
-                    frame_pair(raw[4 * g + 2 * h], pack2(cv.x, cv.y), pack2(yv.x, yv.y), Gi, sp[2 * h], zp[2 * h]);
-                    frame_pair(raw[4 * g + 2 * h + 1], pack2(cv.z, cv.w), pack2(yv.z, yv.w), Gi, sp[2 * h + 1], zp[2 * h + 1]);
-                }
-                Si += trunc_log2<4>(sp, zp);
-            }
-            {   // frames 16, 17
-                u64 sp[1], zp[1];
-                const float2 cv = *reinterpret_cast<const float2*>(crow + 16);
-                const float2 yv = *reinterpret_cast<const float2*>(yrow + 16);
-                frame_pair(raw[8], pack2(cv.x, cv.y), pack2(yv.x, yv.y), Gi, sp[0], zp[0]);
-                Si += trunc_log2<1>(sp, zp);
-            }
-            float ga, gb;
-            unpack2(Gi, ga, gb);
-            const float vi = fmaf(-0.34657359027997264f, Si, -(ga + gb));   // -(ln 2)/2 * log2(prod) - Gaussian term
+            const float vi = block_loglik(raw, crow, yrow);
             v0 += it == 0 ? vi : 0.f;
             v1 += it == 1 ? vi : 0.f;
             v2 += it == 2 ? vi : 0.f;
@@ -518,30 +525,7 @@ __device__ __noinline__ float eval1(const int roi, const float dv, const float a
             const float2 c = *reinterpret_cast<const float2*>(crb + 2 * pq);
             raw[pq] = ffma2r(acc[pq], coefd, fmul2(pack2(c.x, c.y), r1d));
         }
-        u64 Gi = 0ull;
-        float Si = 0.f;
-#pragma unroll
-        for (int g = 0; g < 2; g++) {
-            u64 sp[4], zp[4];
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const float4 cv = *reinterpret_cast<const float4*>(crow + 8 * g + 4 * h);
-                const float4 yv = *reinterpret_cast<const float4*>(yrow + 8 * g + 4 * h);
-                frame_pair(raw[4 * g + 2 * h], pack2(cv.x, cv.y), pack2(yv.x, yv.y), Gi, sp[2 * h], zp[2 * h]);
-                frame_pair(raw[4 * g + 2 * h + 1], pack2(cv.z, cv.w), pack2(yv.z, yv.w), Gi, sp[2 * h + 1], zp[2 * h + 1]);
-            }
-            Si += trunc_log2<4>(sp, zp);
-        }
-        {
-            u64 sp[1], zp[1];
-            const float2 cv = *reinterpret_cast<const float2*>(crow + 16);
-            const float2 yv = *reinterpret_cast<const float2*>(yrow + 16);
-            frame_pair(raw[8], pack2(cv.x, cv.y), pack2(yv.x, yv.y), Gi, sp[0], zp[0]);
-            Si += trunc_log2<1>(sp, zp);
-        }
-        float ga, gb;
-        unpack2(Gi, ga, gb);
-        v += fmaf(-0.34657359027997264f, Si, -(ga + gb));
+        v += block_loglik(raw, crow, yrow);
     }
     return (smem + SM_BAD)[roi] ? -INFINITY : v;
 }
