@@ -180,10 +180,18 @@ __global__ void __launch_bounds__(ESS_LB) rd_ess(const float* xs, const float* z
             for (int c = grp; c < m; c += ESS_LB / ESS_LAGS) {
                 const double mu = cmean[min(c, 2047)];
                 const size_t o = base + (size_t)c * h;
-                double a = 0.0;
-                for (int n = 0; n + t < h; n++)
-                    a += (series(ty, xs, z, a05, a95, o + n) - mu) * (series(ty, xs, z, a05, a95, o + n + t) - mu);
-                acc += a / h;
+                // four independent partial sums: the loop is bound by the latency of the fp64 accumulation chain
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                const int nn = h - t;
+                int n = 0;
+                for (; n + 3 < nn; n += 4) {
+                    a0 += (series(ty, xs, z, a05, a95, o + n) - mu) * (series(ty, xs, z, a05, a95, o + n + t) - mu);
+                    a1 += (series(ty, xs, z, a05, a95, o + n + 1) - mu) * (series(ty, xs, z, a05, a95, o + n + 1 + t) - mu);
+                    a2 += (series(ty, xs, z, a05, a95, o + n + 2) - mu) * (series(ty, xs, z, a05, a95, o + n + 2 + t) - mu);
+                    a3 += (series(ty, xs, z, a05, a95, o + n + 3) - mu) * (series(ty, xs, z, a05, a95, o + n + 3 + t) - mu);
+                }
+                for (; n < nn; n++) a0 += (series(ty, xs, z, a05, a95, o + n) - mu) * (series(ty, xs, z, a05, a95, o + n + t) - mu);
+                acc += ((a0 + a1) + (a2 + a3)) / h;
             }
         }
         part[tid] = acc;
