@@ -66,7 +66,7 @@ struct petmh_handle {
     int last_launches = 0;
     int launch_sweeps = 200;
     int variant = 0;
-    int wide = -1;                // -1 auto, 0 never, 1 always (PETMH_WIDE)
+    int wide = -1;                // -1 auto, 0 never, 1 always three warps per chain pair, 2 always nine (PETMH_WIDE)
 };
 
 static int fail(petmh_t* h, int code, const char* fmt, ...) {
@@ -210,7 +210,7 @@ extern "C" int petmh_create(const petmh_cfg* cfg, petmh_t** out) {
     h->cfg = *cfg;
     if (const char* e = getenv("PETMH_LAUNCH_SWEEPS")) h->launch_sweeps = std::max(1, atoi(e));
     if (const char* e = getenv("PETMH_VARIANT")) h->variant = atoi(e) == 1 ? 1 : 0;
-    if (const char* e = getenv("PETMH_WIDE")) h->wide = atoi(e) ? 1 : 0;
+    if (const char* e = getenv("PETMH_WIDE")) h->wide = std::max(0, std::min(2, atoi(e)));
     auto bail = [&](int code) { petmh_destroy(h); return code; };
 #define CUC(call)                                                                                     \
     do {                                                                                              \
@@ -254,7 +254,8 @@ extern "C" int petmh_create(const petmh_cfg* cfg, petmh_t** out) {
     CUC(cudaFuncSetAttribute(mh_sweep_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(256)));
     CUC(cudaFuncSetAttribute(mh_sweep_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(128)));
     CUC(cudaFuncSetAttribute(mh_sweep_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(256)));
-    CUC(cudaFuncSetAttribute(mh_sweep_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_wide()));
+    CUC(cudaFuncSetAttribute(mh_sweep_kernel<0, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_wide()));
+    CUC(cudaFuncSetAttribute(mh_sweep_kernel<0, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_wide()));
     CUC(cudaFuncSetAttribute(synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_STATE + 32 * SLOTS * NT * 4));
     CUC(cudaFuncSetAttribute(forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_STATE + 32 * SLOTS * NT * 4));
 #undef CUC
@@ -589,11 +590,19 @@ extern "C" int petmh_advance(petmh_t* h, int n_sweeps) {
     if (n_sweeps < 0) return fail(h, PETMH_EINVAL, "n_sweeps < 0");
     if (!h->state_ready) return fail(h, PETMH_EINVAL, "chain state not initialised: call petmh_reset, petmh_run or petmh_set_state first");
     CU(cudaSetDevice(h->cfg.device));
-    // small jobs: the wide kernel (three warps per chain pair) when even that leaves SMs to spare
+    // small jobs: the wide kernels when even they leave SMs to spare -- nine warps per chain pair (one pair per CTA)
+    // while every pair gets its own SM, three warps per pair (up to four pairs per CTA) while one wave holds them all
     const size_t pairs = (size_t)h->n_tac * ((h->cfg.n_chains + 1) / 2);
-    const bool wide = h->variant == 0 && (h->wide == 1 || (h->wide < 0 && pairs <= (size_t)WIDE_MAX_TRIPLES * 148));   // one wave
+    int wide = 0;
+    if (h->variant == 0) {
+        if (h->wide > 0) wide = h->wide;
+        else if (h->wide < 0) wide = pairs <= 148 ? 2 : (pairs <= (size_t)WIDE_MAX_TRIPLES * 148 ? 1 : 0);
+    }
     int nthr, chains_per_cta;
-    if (wide) {
+    if (wide == 2) {
+        nthr = 288;
+        chains_per_cta = 2;
+    } else if (wide) {
         int triples = 1;   // per CTA: one unless the CTAs would outnumber the SMs
         while (triples < WIDE_MAX_TRIPLES && (size_t)h->n_tac * ((h->cfg.n_chains + 2 * triples - 1) / (2 * triples)) > 148) triples *= 2;
         nthr = 96 * triples;
@@ -622,7 +631,8 @@ extern "C" int petmh_advance(petmh_t* h, int n_sweeps) {
         const int half = (drawing && h->sweep >= half_at) ? 1 : 0;
         p.mom_half = half;
         p.mom_n_before = h->mom_n[half];
-        if (wide) mh_sweep_kernel<0, false, true><<<grid, nthr, smem_bytes_wide(), h->stream>>>(p);
+        if (wide == 2) mh_sweep_kernel<0, false, 2><<<grid, nthr, smem_bytes_wide(), h->stream>>>(p);
+        else if (wide) mh_sweep_kernel<0, false, 1><<<grid, nthr, smem_bytes_wide(), h->stream>>>(p);
         else if (h->variant == 0) mh_sweep_kernel<0, false><<<grid, nthr, smem_bytes(256), h->stream>>>(p);
         else mh_sweep_kernel<1, false><<<grid, nthr, smem_bytes(128), h->stream>>>(p);
         CU(cudaGetLastError());

@@ -178,6 +178,22 @@ __device__ __forceinline__ float u01(uint32_t x) {  // (0, 1]
     return fmaf(__uint2float_rn(x), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
 }
 
+// The random numbers of one coordinate update (coordinate i of block b in sweep `sweep` of chain gid): proposal
+// normal, log-uniform and visit key from ONE Philox call.  One routine for every path that draws them.
+__device__ __forceinline__ void draw_randoms(unsigned long long seed, unsigned long long gid, int sweep, int b, int i,
+                                             float& nrm, float& logu, uint32_t& key) {
+    // (opaque copies: otherwise the loop-invariant first-round products of the coordinate and chain
+    // words are hoisted out of the sweep loop and spilled -- reloading them costs more than 2 IMAD)
+    uint32_t ci = (uint32_t)i, glo = (uint32_t)gid;
+    asm volatile("" : "+r"(ci), "+r"(glo));
+    const uint4 x = philox4x32_10(make_uint4(ci, (uint32_t)(2 * sweep + b), glo, (uint32_t)(gid >> 32)),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    // Box-Muller (cos branch) with MUFU lg2 / sqrt / cos; ln u = lg2(u) * ln 2
+    nrm = sqrt_approx(-1.3862943611198906f * lg2_approx(u01(x.x))) * cos_approx(6.283185307179586f * u01(x.y));
+    logu = 0.6931471805599453f * lg2_approx(u01(x.z));
+    key = (x.w & 0xffffffc0u) | 0x80000000u | (uint32_t)i;   // > 0, unique, random order
+}
+
 // ------------------------------------------------------------------------------------
 // 0.5 * erfc(z), z >= 0: t exp(-z^2) Q(t), t = 1/(1 + p z)   (tools/fit_erfc.py, |err| < 2e-7 in fp32)
 // ------------------------------------------------------------------------------------
@@ -476,9 +492,10 @@ __device__ PETMH_EVAL3_INLINE float3 eval3(const int l16, const float d0, const 
     return make_float3(bad[l16] ? -INFINITY : v0, bad[l16 + 16] ? -INFINITY : v1, bad[l16 + 32] ? -INFINITY : v2);
 }
 
-// One item per lane (the "wide" small-job path: the three ROI slots of a lane are evaluated by three warps).
-// Per item the operations and their order are exactly those of eval3, so the results are bit-identical.
-__device__ __noinline__ float eval1(const int roi, const float dv, const float av) {
+// One item per lane (the "wide" small-job paths: the three ROI slots of a lane -- and, in the nine-warp variant, the
+// three row blocks of a slot -- are evaluated by different warps).  Per item the operations and their order are exactly
+// those of eval3, so the results are bit-identical.  eval1_block = one row block's share of the log-likelihood.
+__device__ __forceinline__ float eval1_block(const int roi, const float dv, const float av, const int blk) {
     extern __shared__ __align__(16) unsigned char smem[];
     const float* sM = reinterpret_cast<const float*>(smem + SM_M);
     const float* sCr = reinterpret_cast<const float*>(smem + SM_CR);
@@ -489,9 +506,7 @@ __device__ __noinline__ float eval1(const int roi, const float dv, const float a
     const float* yrow0 = reinterpret_cast<const float*>(smem + SM_YCC) + roi * YS;
     const float* crow0 = reinterpret_cast<const float*>(smem + SM_CC) + roi * YS;
     const u64 coefd = pack2(coef, coef), r1d = pack2(av, av);
-    float v = 0.f;
-#pragma unroll 1
-    for (int blk = 0; blk < NBLK; blk++) {
+    {
         const float4* Mp = reinterpret_cast<const float4*>(sM + (blk == 0 ? 0 : (blk == 1 ? 220 : 780)));   // PETMH_MOFF
         u64 acc[NPAIR];
 #pragma unroll
@@ -525,9 +540,18 @@ __device__ __noinline__ float eval1(const int roi, const float dv, const float a
             const float2 c = *reinterpret_cast<const float2*>(crb + 2 * pq);
             raw[pq] = ffma2r(acc[pq], coefd, fmul2(pack2(c.x, c.y), r1d));
         }
-        v += block_loglik(raw, crow, yrow);
+        return block_loglik(raw, crow, yrow);
     }
+}
+__device__ __noinline__ float eval1(const int roi, const float dv, const float av) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float v = 0.f;
+#pragma unroll 1
+    for (int blk = 0; blk < NBLK; blk++) v += eval1_block(roi, dv, av, blk);
     return (smem + SM_BAD)[roi] ? -INFINITY : v;
+}
+__device__ __noinline__ float eval1_blk(const int roi, const float dv, const float av, const int blk) {
+    return eval1_block(roi, dv, av, blk);
 }
 
 // ------------------------------------------------------------------------------------
@@ -639,23 +663,28 @@ __host__ __device__ constexpr int smem_bytes(int nthreads) { return SM_STATE + S
 // kernel, but the log-likelihood of ROI slot s is evaluated by the triple's warp s (eval1) -- arguments and results
 // cross through a small shared-memory mailbox and one named barrier per triple.  Same arithmetic per item, same
 // random numbers: the chains are bit-identical to the normal path's.
+// WIDE = 2 (the smallest jobs: at most one chain pair per SM): nine warps per chain pair, warp r evaluates row block
+// r % 3 of ROI slot r / 3 (eval1_blk) and the leader adds the three partial sums of a slot in eval1's order.
 constexpr int WIDE_MAX_TRIPLES = 4;
-constexpr int XCH_WORDS = 9;   // d[3], a[3], ll[3] per lane
-__device__ __forceinline__ void triple_barrier(int triple) {
-    asm volatile("bar.sync %0, 96;" ::"r"(1 + triple) : "memory");
+constexpr int XCH_WORDS = 15;   // d[3], a[3], then ll[3] (WIDE 1) or partial ll[3 slots][3 blocks] (WIDE 2), per lane
+template <int NTHREADS>
+__device__ __forceinline__ void group_barrier(int group) {
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(NTHREADS) : "memory");
 }
 __host__ __device__ constexpr int smem_bytes_wide() { return smem_bytes(256) + WIDE_MAX_TRIPLES * XCH_WORDS * 32 * 4; }
 
-template <int VARIANT, bool TAPED, bool WIDE = false>
-__global__ void __launch_bounds__(WIDE ? 96 * WIDE_MAX_TRIPLES : (VARIANT == 0 ? 256 : 128), WIDE ? 1 : (VARIANT == 0 ? 2 : 3))
+template <int VARIANT, bool TAPED, int WIDE = 0>
+__global__ void __launch_bounds__(WIDE == 2 ? 288 : (WIDE == 1 ? 96 * WIDE_MAX_TRIPLES : (VARIANT == 0 ? 256 : 128)),
+                                  WIDE ? 1 : (VARIANT == 0 ? 2 : 3))
     mh_sweep_kernel(const SweepParams p) {
+    constexpr int GW = WIDE == 2 ? 9 : 3;   // warps per chain pair in the wide variants
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31;
-    const int triple = WIDE ? (tid >> 5) / 3 : 0, role = WIDE ? (tid >> 5) % 3 : 0;
+    const int triple = WIDE ? (tid >> 5) / GW : 0, role = WIDE ? (tid >> 5) % GW : 0;
     const int warp = WIDE ? triple : (tid >> 5);   // index of the chain pair within the CTA
     const int half = lane >> 4, l16 = lane & 15;
-    const int chains_per_cta = WIDE ? (nthr / 96) * 2 : (nthr >> 4);
+    const int chains_per_cta = WIDE ? (nthr / (32 * GW)) * 2 : (nthr >> 4);
     const int groups_per_tac = (p.n_chains + chains_per_cta - 1) / chains_per_cta;
     const int tac = TAPED ? p.tape_tac : (int)(blockIdx.x / groups_per_tac);
     const int grp = TAPED ? (int)blockIdx.x : (int)(blockIdx.x % groups_per_tac);
@@ -667,14 +696,16 @@ __global__ void __launch_bounds__(WIDE ? 96 * WIDE_MAX_TRIPLES : (VARIANT == 0 ?
     float* xch = reinterpret_cast<float*>(smem + smem_bytes(256)) + triple * XCH_WORDS * 32 + lane;   // WIDE mailbox
 
     load_tac_image(p, tac, smem, tid, nthr);
-    if (WIDE && role != 0) {   // helper warp: evaluate slot `role` for the leader, once per eval site visit
+    if (WIDE && role != 0) {   // helper warp: evaluate its share for the leader, once per eval site visit
         const int n_eval = 1 + 2 * p.n_sweeps;
+        const int hs = WIDE == 2 ? role / 3 : role, hk = role % 3;   // ROI slot (and row block, WIDE 2)
 #pragma unroll 1
         for (int n = 0; n < n_eval; n++) {
-            triple_barrier(triple);
-            const float ll = eval1(l16 + 16 * role, xch[role * 32], xch[(3 + role) * 32]);
+            group_barrier<32 * GW>(triple);
+            const float dv = xch[hs * 32], av = xch[(3 + hs) * 32];
+            const float ll = WIDE == 2 ? eval1_blk(l16 + 16 * hs, dv, av, hk) : eval1(l16 + 16 * hs, dv, av);
             xch[(6 + role) * 32] = ll;
-            triple_barrier(triple);
+            group_barrier<32 * GW>(triple);
         }
         return;
     }
@@ -683,9 +714,16 @@ __global__ void __launch_bounds__(WIDE ? 96 * WIDE_MAX_TRIPLES : (VARIANT == 0 ?
         if (WIDE) {
             xch[0 * 32] = d0; xch[1 * 32] = d1; xch[2 * 32] = d2;
             xch[3 * 32] = a0; xch[4 * 32] = a1; xch[5 * 32] = a2;
-            triple_barrier(triple);
-            const float v0 = eval1(l16, d0, a0);
-            triple_barrier(triple);
+            group_barrier<32 * GW>(triple);
+            const float v0 = WIDE == 2 ? eval1_blk(l16, d0, a0, 0) : eval1(l16, d0, a0);
+            group_barrier<32 * GW>(triple);
+            if (WIDE == 2) {   // (0 + b0) + b1) + b2 per slot, as eval1 accumulates; then the TAC's bad-observation flag
+                const unsigned char* bad = smem + SM_BAD;
+                const float s0 = ((0.f + v0) + xch[7 * 32]) + xch[8 * 32];
+                const float s1 = ((0.f + xch[9 * 32]) + xch[10 * 32]) + xch[11 * 32];
+                const float s2 = ((0.f + xch[12 * 32]) + xch[13 * 32]) + xch[14 * 32];
+                return make_float3(bad[l16] ? -INFINITY : s0, bad[l16 + 16] ? -INFINITY : s1, bad[l16 + 32] ? -INFINITY : s2);
+            }
             return make_float3(v0, xch[7 * 32], xch[8 * 32]);
         }
         return eval3<VARIANT>(l16, d0, d1, d2, a0, a1, a2, nullptr);
@@ -771,16 +809,7 @@ __global__ void __launch_bounds__(WIDE ? 96 * WIDE_MAX_TRIPLES : (VARIANT == 0 ?
                     logu[s] = active ? p.tape_logu[o] : 0.f;
                     key[s] = (((active ? (uint32_t)p.tape_rank[o] : (uint32_t)i) + 1u) << 6) | (uint32_t)i;
                 } else {
-                    // (opaque copies: otherwise the loop-invariant first-round products of the coordinate and chain
-                    // words are hoisted out of the sweep loop and spilled -- reloading them costs more than 2 IMAD)
-                    uint32_t ci = (uint32_t)i, glo = (uint32_t)gid;
-                    asm volatile("" : "+r"(ci), "+r"(glo));
-                    const uint4 x = philox4x32_10(make_uint4(ci, (uint32_t)(2 * sweep + b), glo, (uint32_t)(gid >> 32)),
-                                                  make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
-                    // Box-Muller (cos branch) with MUFU lg2 / sqrt / cos; ln u = lg2(u) * ln 2
-                    nrm = sqrt_approx(-1.3862943611198906f * lg2_approx(u01(x.x))) * cos_approx(6.283185307179586f * u01(x.y));
-                    logu[s] = 0.6931471805599453f * lg2_approx(u01(x.z));
-                    key[s] = (x.w & 0xffffffc0u) | 0x80000000u | (uint32_t)i;   // > 0, unique, random order
+                    draw_randoms(p.seed, gid, sweep, b, i, nrm, logu[s], key[s]);
                 }
                 q[s] = ST_F(sb + s);
                 qn[s] = __fadd_rn(q[s], __fmul_rn(nrm, sc));          // q' = fl32(q + fl32(n * scale))

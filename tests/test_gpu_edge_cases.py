@@ -146,12 +146,13 @@ def test_large_batch_shard_invariance_and_determinism(dataset, prior):
 
 
 def test_wide_small_job_path_is_bit_identical(dataset, prior, monkeypatch):
-    """Small jobs run the wide kernel (three warps per chain pair, one ROI slot each; petmh_device.cuh WIDE):
-    same random numbers, same per-item arithmetic -> chains, summaries and resumed state equal the normal
-    kernel's bit for bit.  Covers a ragged chain count (odd: half of the last pair idles) and CTAs of 1..4 triples."""
+    """Small jobs run the wide kernels (petmh_device.cuh WIDE: 1 = three warps per chain pair, one ROI slot each;
+    2 = nine warps per pair, one row block of one slot each): same random numbers, same per-item arithmetic ->
+    chains, summaries and resumed state equal the normal kernel's bit for bit.  Covers a ragged chain count (odd:
+    half of the last pair idles) and CTAs of 1..4 triples."""
     for n_chains, tacs in [(5, [0, 1]), (64, [2]), (16, list(range(24))), (32, list(range(20)))]:
         out = {}
-        for wide in ("0", "1"):
+        for wide in ("0", "1", "2"):
             monkeypatch.setenv("PETMH_WIDE", wide)
             s = make_sampler(dataset, prior, n_chains=n_chains, max_draws=40, seed=11, tacs=[t % 4 for t in tacs])
             s.run(draws=40, tune=230)            # crosses two tuning boundaries and the 200-sweep launch chunk
@@ -159,6 +160,7 @@ def test_wide_small_job_path_is_bit_identical(dataset, prior, monkeypatch):
             q, sc = s.state()
             out[wide] = (dvr.copy(), r1.copy(), q.copy(), sc.copy(), s.summary().copy())
             s.close()
-        for a, b in zip(out["0"], out["1"]):
-            assert np.array_equal(a, b, equal_nan=True)
+        for w in ("1", "2"):
+            for a, b in zip(out["0"], out[w]):
+                assert np.array_equal(a, b, equal_nan=True)
         assert np.isfinite(out["1"][0]).all()
