@@ -570,16 +570,20 @@ static int threads_per_cta(const petmh_t* h) {
     int t = h->cfg.n_chains * 16;
     t = (t + 31) / 32 * 32;
     t = std::min(t, h->variant == 0 ? 256 : 128);
-    // small jobs (e.g. one TAC x 64 chains): spread the chains over more, smaller CTAs so that every SM gets a
-    // warp -- the sweep loop is latency-bound per warp, and an under-filled GPU has SMs to spare.  CTA sizes stay
-    // whole warps: shrink through powers of two only (96 -> 64 -> 32, never 48).
+    // Jobs of less than one wave (2 CTAs x 148 SMs; e.g. 12 TACs x 256 chains, or one TAC x 64 chains when the wide
+    // kernels are off): every CTA is resident at once, so the time is that of the busiest SM -- the sweep loop is
+    // latency-bound per warp.  Pick the CTA size (whole warps = chain pairs, any multiple of 32 threads) that minimises
+    // ceil(CTAs / 148) x warps per CTA while all CTAs still fit one wave; ties go to the smaller CTA (more SMs in use).
     auto groups = [&](int tt) { return (size_t)h->n_tac * ((h->cfg.n_chains * 16 + tt - 1) / tt); };
-    // ... and only while the smaller CTAs are still all resident at once (2 per SM): a second wave costs more
-    if (t > 32 && groups(t) < 2 * 148) {
-        int pw = 32;
-        while (pw * 2 <= t) pw *= 2;
-        if (groups(pw) <= 2 * 148) t = pw;
-        while (t > 32 && (t & (t - 1)) == 0 && groups(t / 2) <= 2 * 148) t /= 2;
+    if (groups(t) < 2 * 148) {
+        auto cost = [&](int tt) { return (long)((groups(tt) + 147) / 148) * tt; };
+        int best = t;
+        long best_cost = cost(t);
+        for (int tt = t - 32; tt >= 32; tt -= 32) {
+            if (groups(tt) > 2 * 148) break;
+            if (cost(tt) <= best_cost) { best = tt; best_cost = cost(tt); }
+        }
+        t = best;
     }
     return t;
 }

@@ -29,6 +29,17 @@ def test_chain_streams_do_not_depend_on_chain_count(dataset, prior, monkeypatch)
         for C in (1, 3, 4, 5, 6, 10):
             assert np.array_equal(runs[C][0][0], ref[0][0, :C]) and np.array_equal(runs[C][1][0], ref[1][0, :C]), C
         assert not np.array_equal(ref[0][0, 0], ref[0][0, 1])
+    # sub-wave jobs of several TACs pick odd CTA sizes (petmh.cu threads_per_cta: any multiple of 32 threads)
+    monkeypatch.setenv("PETMH_WIDE", "0")
+    big = {}
+    for C in (22, 44, 52):
+        s = make_sampler(dataset, prior, n_chains=C, max_draws=10, seed=5, tacs=[0, 1, 2, 3, 0, 1, 2])
+        s.run(draws=10, tune=120)
+        big[C] = s.chains()
+        s.close()
+    for C in (22, 44):   # (gid = TAC index * n_chains + chain: only TAC 0's streams are independent of n_chains)
+        assert np.array_equal(big[C][0][0], big[52][0][0, :C]) and np.array_equal(big[C][1][0], big[52][1][0, :C]), C
+        assert np.isfinite(big[C][0]).all()
 
 
 def test_thinning_and_capacity(dataset, prior):
