@@ -246,12 +246,11 @@ constexpr int K = SLOTS;
 // Two consecutive frames of one item in packed fp32x2 arithmetic (FMUL2 / FFMA2):
 // TAC assembly (kinetic_model.py:157-158), clamp (mcmc.py:152), Gaussian term, z = sqrt(s)/(sig sqrt2).
 //   convp = {conv_f, conv_f+1}, crp = c_r pair, ccp = 1/(sig sqrt2) pair, nyp = -(y/(sig sqrt2)) pair
+//   raw = the CLAMPED TAC pair (block_loglik applies mcmc.py:152's switch(sn < 0, 1e-6, sn) up front)
 __device__ __forceinline__ void frame_pair(const u64 raw, const u64 ccp, const u64 nyp, u64& Gp, u64& sp, u64& zp) {
     float s0, s1;
     unpack2(raw, s0, s1);
-    s0 = s0 < 0.f ? 1e-6f : s0;
-    s1 = s1 < 0.f ? 1e-6f : s1;
-    sp = pack2(s0, s1);
+    sp = raw;
     const u64 rsp = pack2(rsqrt_approx(s0), rsqrt_approx(s1));
     const u64 up = fmul2(ffma2r(sp, ccp, nyp), rsp);          // (s - y) / (sig sqrt(2 s))
     Gp = ffma2r(up, up, Gp);                                   // (y-s)^2 / (2 s sig^2)
@@ -322,8 +321,38 @@ __device__ __forceinline__ float trunc_log2(const u64* __restrict__ sp, const u6
 
 // Log-likelihood (reduced, natural log) of one item's 18 frames of a row block from its unclamped TAC pairs.
 // One routine for eval3 and eval1: the operations and their order per item are the same on every path.
-__device__ __forceinline__ float block_loglik(const u64 (&raw)[NPAIR], const float* __restrict__ crow,
+#ifndef PETMH_CLAMP_VOTE
+#define PETMH_CLAMP_VOTE 1
+#endif
+__device__ __forceinline__ float block_loglik(const u64 (&raw_in)[NPAIR], const float* __restrict__ crow,
                                               const float* __restrict__ yrow) {
+    // clamp (mcmc.py:152): a model TAC is negative only for wild proposals, so one warp-uniform vote on the minimum of
+    // the 18 values skips the 36 compare/select instructions otherwise (identity for s >= 0 and for NaN, as before)
+    u64 raw[NPAIR];
+    bool need_clamp = true;
+    if (PETMH_CLAMP_VOTE) {
+        float mn = CUDART_INF_F;
+#pragma unroll
+        for (int pq = 0; pq < NPAIR; pq++) {
+            float a, b;
+            unpack2(raw_in[pq], a, b);
+            mn = fminf(mn, fminf(a, b));
+        }
+        need_clamp = __any_sync(0xffffffffu, mn < 0.f);
+    }
+    if (need_clamp) {
+#pragma unroll
+        for (int pq = 0; pq < NPAIR; pq++) {
+            float a, b;
+            unpack2(raw_in[pq], a, b);
+            a = a < 0.f ? 1e-6f : a;
+            b = b < 0.f ? 1e-6f : b;
+            raw[pq] = pack2(a, b);
+        }
+    } else {
+#pragma unroll
+        for (int pq = 0; pq < NPAIR; pq++) raw[pq] = raw_in[pq];
+    }
     u64 Gi = 0ull;
     float Si = 0.f;
 #pragma unroll
