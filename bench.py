@@ -349,7 +349,9 @@ def run_b200(args):
                          "traffic": 18610574336 if (S == 131072 and SW == 100) else None,
                          "note": "dominant kernel mh_sweep_kernel (%.1f %% of the step by CUDA events on its stream); achieved = "
                                  "3980 algorithmic FP32 flop/chain-step x per-GPU kernel rate; peak = 148 SM x 128 lanes x 2 x SM clock "
-                                 "under load (nominal formula: MEASURED_PEAKS.json has no FP32 figure)" % (100 * dev_s / wall_s),
+                                 "under load (nominal formula: MEASURED_PEAKS.json has no FP32 figure); pipe utilisation of the same kernel "
+                                 "in its tuned steady state under ncu (profiles/r01_ncu_sweep_tuned_inlined_summary.txt): FMA pipe 54 %%, "
+                                 "XU/MUFU 42 %%, issue slots 62 %%" % (100 * dev_s / wall_s),
                          "sfu_frac": kern_rate_1gpu * SFU_ALG / peak_sfu,
                          "kernel_chain_steps_per_s_per_gpu": kern_rate_1gpu},
             "cpu_baseline": cpu,
