@@ -333,7 +333,8 @@ def run_b200(args):
             "data": "synthetic: %d unique SRTM2 TACs per rank generated on the GPU (K4 petmh_synth: restated sample_sim_data.py training-style priors, sigma 0.1)" % S,
             "config": {"workload": "BASELINE configs[4] throughput scaling, TAC-sharded: %d TACs/GPU x %d chains x 48 ROIs "
                                    "(1M TACs at 8 GPUs); step = %d sweeps (x96 chain-steps) of every chain, draw phase after "
-                                   "%d tuning sweeps" % (S, C, SW, TUNE),
+                                   "%d tuning sweeps (chains whose PyMC scaling has fully settled, 5000+ tuning sweeps, accept more "
+                                   "moves and run ~4 %% slower: more visit-order rounds)" % (S, C, SW, TUNE),
                        "tacs_per_gpu": S, "chains_per_tac": C, "sweeps_per_step": SW, "chain_steps_per_step": steps_per_step,
                        "l2_policy": "per-step working set (inputs+state %.1f GB) >> 126 MB L2" % ((S * 10588 + S * C * 3500) / 1e9),
                        "sec_per_48roi_posterior_60000_sweeps_amortised": 60000 * 96 * C / (value / world) ,
