@@ -134,8 +134,11 @@ __global__ void rd_rhat(const float* z, const float* zf, int m, int h, float* rh
 
 // arviz _ess for one (segment, series type); blockDim.x = ESS_LB lags per batch
 constexpr int ESS_LB = 256, ESS_LAGS = 64;
+constexpr int ESS_STAGE_MAX_H = 6144;   // 4 chain groups x h floats of dynamic shared memory (<= 96 KB)
 __global__ void __launch_bounds__(ESS_LB) rd_ess(const float* xs, const float* z, const float* q05, const float* q95, int m,
-                                                 int h, float* rho_scratch /*[nseg*4][h]*/, float* ess_out /*[nseg][4]*/) {
+                                                 int h, float* rho_scratch /*[nseg*4][h]*/, float* ess_out /*[nseg][4]*/,
+                                                 int staged /* dynamic smem holds 4 x h floats */) {
+    extern __shared__ float ess_stage[];   // [chain group][h]: the centred series of the chain the group is working on
     __shared__ double sh[32];
     __shared__ double cmean[2048];
     __shared__ int s_stop, s_t;
@@ -176,7 +179,42 @@ __global__ void __launch_bounds__(ESS_LB) rd_ess(const float* xs, const float* z
         // compute lags have+1 .. have+ESS_LAGS
         const int t = have + 1 + tl;
         double acc = 0.0;
-        if (t < h) {
+        if (staged) {
+            // Staged path: each group centres its chain once per batch into shared memory as fp32 (the draws are fp32:
+            // rounding x - mean to fp32 is below their own quantisation) and forms the lag products with fp32 FMAs in
+            // chunks of 8, added up in fp64 -- one LDS + one FFMA per product instead of two conversions, two fp64
+            // subtractions and a DFMA (the loop was bound by the FP64 pipe).  Uniform trip count: barriers inside.
+            constexpr int NG = ESS_LB / ESS_LAGS;
+            float* cb = ess_stage + (size_t)grp * h;
+            for (int c0 = 0; c0 < m; c0 += NG) {
+                const int c = c0 + grp;
+                __syncthreads();
+                if (c < m) {
+                    const double mu = cmean[min(c, 2047)];
+                    const size_t o = base + (size_t)c * h;
+                    for (int i = tl; i < h; i += ESS_LAGS) cb[i] = (float)((double)series(ty, xs, z, a05, a95, o + i) - mu);
+                }
+                __syncthreads();
+                if (c < m && t < h) {
+                    const int nn = h - t;
+                    const float* ca = cb;
+                    const float* cl = cb + t;
+                    double a = 0.0;
+                    int n = 0;
+                    for (; n + 15 < nn; n += 16) {
+                        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            s0 = fmaf(ca[n + u], cl[n + u], s0);
+                            s1 = fmaf(ca[n + 8 + u], cl[n + 8 + u], s1);
+                        }
+                        a += (double)s0 + (double)s1;
+                    }
+                    for (; n < nn; n++) a += (double)(ca[n] * cl[n]);
+                    acc += a / h;
+                }
+            }
+        } else if (t < h) {
             for (int c = grp; c < m; c += ESS_LB / ESS_LAGS) {
                 const double mu = cmean[min(c, 2047)];
                 const size_t o = base + (size_t)c * h;
@@ -318,7 +356,12 @@ static inline int launch_rank_summary(const float* d_draws, int n_tac_total, int
             RD(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k0, k1, v0, v1, n, 0, 32 + seg_bits, st));
             rd_ranks<<<gb, 256, 0, st>>>(k1, v1, zf, L, n);
             rd_rhat<<<nseg, 256, 0, st>>>(z, zf, m, h, rhat);
-            rd_ess<<<nseg * 4, ESS_LB, 0, st>>>(xs, z, q05, q95, m, h, rho, ess);
+            {
+                const int staged = h <= ESS_STAGE_MAX_H ? 1 : 0;
+                const size_t dyn = staged ? (size_t)(ESS_LB / ESS_LAGS) * h * sizeof(float) : 0;
+                if (dyn > 16 * 1024) RD(cudaFuncSetAttribute(rd_ess, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                rd_ess<<<nseg * 4, ESS_LB, dyn, st>>>(xs, z, q05, q95, m, h, rho, ess, staged);
+            }
             rd_finalize<<<nseg, 256, 0, st>>>(xs, L, ess, rhat, nacc, scale, n_chains, t0, n_draw_sweeps, d_out);
             RD(cudaGetLastError());
         }
