@@ -100,6 +100,11 @@ int petmh_loglik(petmh_t* h, int tac, const double* dvr48, const double* r1_48, 
 /* the device-built exact convolution operator M (54x54) of estimate_continuous_convolution
  * (kinetic_model.py:12-32): conv = M @ exp(-k2a t). */
 int petmh_get_operator(petmh_t* h, int tac, double* m54x54);
+/* the Chebyshev-in-k2a form of the same operator that the sweep kernel evaluates:
+ * conv[j] = sum_d A[j][d] T_d(s), s = (2 k2a - k2a_lo - k2a_hi) / (k2a_hi - k2a_lo), valid for k2a in [k2a_lo, k2a_hi]
+ * (outside it the kernel uses M itself).  a[520] f32 is laid out [3 row blocks of 18 frames][ncols3[b] columns][20]
+ * (18 rows + 2 pad).  Any output pointer may be NULL.  Replaces the same lines as petmh_get_operator. */
+int petmh_get_cheb_operator(petmh_t* h, int tac, float* a520, int* ncols3, double* k2a_lo, double* k2a_hi);
 /* raw Philox4x32-10 words the kernel draws for (chain gid, sweep, block): out[48][4] */
 int petmh_philox_raw(petmh_t* h, uint64_t chain_gid, uint32_t sweep, uint32_t block, uint32_t* out48x4);
 

@@ -48,6 +48,7 @@ def _load():
         "petmh_forward_srtm": (C.c_int, [H, C.c_int, dp, dp, dp, dp]),
         "petmh_loglik": (C.c_int, [H, C.c_int, dp, dp, dp, dp]),
         "petmh_get_operator": (C.c_int, [H, C.c_int, dp]),
+        "petmh_get_cheb_operator": (C.c_int, [H, C.c_int, fp, C.POINTER(C.c_int), dp, dp]),
         "petmh_philox_raw": (C.c_int, [H, C.c_uint64, C.c_uint32, C.c_uint32, u32p]),
         "petmh_reset": (C.c_int, [H]),
         "petmh_run": (C.c_int, [H, C.c_int, C.c_int, C.c_int]),

@@ -17,6 +17,8 @@
 using namespace petmh;
 
 static std::string g_create_error;
+// dynamic shared memory of the one-CTA hook / generator kernels: the TAC image + max(prologue scratch, 32 lanes x 3 x 54 TAC values)
+static constexpr int HOOK_SMEM = SM_STATE + (TMP_BYTES > 32 * SLOTS * NT * 4 ? TMP_BYTES : 32 * SLOTS * NT * 4);
 
 struct petmh_handle {
     petmh_cfg cfg{};
@@ -107,6 +109,20 @@ static void two_tap(const double* xp, int np, double x, int& ia, double& wa, int
     ib = hi; wb = w_hi / s;
 }
 
+// Modified Bessel function I_d(x), x >= 0 moderate (h t <= ~3): ascending series, fp64.
+static double bessel_i(int d, double x) {
+    const double hx = 0.5 * x, q = hx * hx;
+    double term = 1.0;
+    for (int k = 1; k <= d; k++) term *= hx / k;          // (x/2)^d / d!
+    double sum = term;
+    for (int m = 1; m < 200; m++) {
+        term *= q / ((double)m * (double)(m + d));
+        sum += term;
+        if (term <= 1e-18 * sum) break;
+    }
+    return sum;
+}
+
 static int build_frame_tables(petmh_t* h, const double* t) {
     FrameTables& ft = h->ft_host;
     double tmin = t[0], tmax = t[0];
@@ -156,6 +172,21 @@ static int build_frame_tables(petmh_t* h, const double* t) {
                         "compiled 54-frame schedule (tools/gen_schedule.py)", j);
     }
     for (int c = 0; c < NCOL; c++) { ft.acol[c] = acol_c[c]; h->tcol[c] = (float)t[acol_c[c]]; }
+    for (int j = 0; j < NT; j++) ft.nrow[j] = nrow_c[j];
+    // Chebyshev table C[f][d] = c_d (-1)^d e^{-kmid t_f} I_d(h t_f) (c_0 = 1, c_d = 2) for the range the kernel's fp32
+    // s = k2a * inv_h - C0 maps to [-1, 1]: k2a t_last in [CHEB_KT_LO, CHEB_KT_HI]
+    {
+        const double h0 = 0.5 * (CHEB_KT_HI - CHEB_KT_LO) / tmax;
+        ft.inv_h = (float)(1.0 / h0);
+        const double hh = 1.0 / (double)ft.inv_h, kmid = (double)CHEB_C0 * hh;
+        for (int c = 0; c < NCOL; c++) {
+            const double tf = t[acol_c[c]], e = std::exp(-kmid * tf);
+            for (int d = 0; d < NCHMAX; d++) {
+                const double v = e * bessel_i(d, hh * tf);
+                ft.cheb_c[c][d] = (d == 0 ? 1.0 : 2.0) * ((d & 1) ? -v : v);
+            }
+        }
+    }
     for (int i = 0; i < MPACK; i++) ft.pack_src[i] = pack_c[i];
     return PETMH_OK;
 }
@@ -256,8 +287,9 @@ extern "C" int petmh_create(const petmh_cfg* cfg, petmh_t** out) {
     CUC(cudaFuncSetAttribute(mh_sweep_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(256)));
     CUC(cudaFuncSetAttribute(mh_sweep_kernel<0, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_wide()));
     CUC(cudaFuncSetAttribute(mh_sweep_kernel<0, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_wide()));
-    CUC(cudaFuncSetAttribute(synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_STATE + 32 * SLOTS * NT * 4));
-    CUC(cudaFuncSetAttribute(forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_STATE + 32 * SLOTS * NT * 4));
+    CUC(cudaFuncSetAttribute(synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HOOK_SMEM));
+    CUC(cudaFuncSetAttribute(forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HOOK_SMEM));
+    CUC(cudaFuncSetAttribute(cheb_operator_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HOOK_SMEM));
 #undef CUC
     *out = h;
     return PETMH_OK;
@@ -455,7 +487,7 @@ static int run_forward(petmh_t* h, int tac, const double* dvr, const double* r1,
     float* d_in = h->d_scratch + 48 * NT + 64;
     CU(cudaMemcpyAsync(d_in, in, sizeof in, cudaMemcpyHostToDevice, h->stream));
     SweepParams p = base_params(h);
-    forward_kernel<<<1, 64, SM_STATE + 32 * SLOTS * NT * 4, h->stream>>>(p, tac, d_in, d_in + 48, h->d_scratch, h->d_scratch + 48 * NT);
+    forward_kernel<<<1, 64, HOOK_SMEM, h->stream>>>(p, tac, d_in, d_in + 48, h->d_scratch, h->d_scratch + 48 * NT);
     CU(cudaGetLastError());
     tac_out.resize(48 * NT);
     ll_out.resize(48);
@@ -527,6 +559,26 @@ extern "C" int petmh_get_operator(petmh_t* h, int tac, double* m) {
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(m, h->d_scratch64, NT * NT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    return PETMH_OK;
+}
+
+extern "C" int petmh_get_cheb_operator(petmh_t* h, int tac, float* a, int* ncols3, double* k2a_lo, double* k2a_hi) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (tac < 0 || tac >= h->n_tac) return fail(h, PETMH_EINVAL, "bad argument");
+    CU(cudaSetDevice(h->cfg.device));
+    if (a) {
+        SweepParams p = base_params(h);
+        cheb_operator_kernel<<<1, 64, HOOK_SMEM, h->stream>>>(p, tac, h->d_scratch);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(a, h->d_scratch, (NCH0 + NCH1 + NCH2) * RSTRIDE * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    if (ncols3) { ncols3[0] = NCH0; ncols3[1] = NCH1; ncols3[2] = NCH2; }
+    // the range the kernel's fp32 s = k2a * inv_h - C0 maps to [-1, 1]
+    const double hh = 1.0 / (double)h->ft_host.inv_h, kmid = (double)CHEB_C0 * hh;
+    if (k2a_lo) *k2a_lo = kmid - hh;
+    if (k2a_hi) *k2a_hi = kmid + hh;
     return PETMH_OK;
 }
 
@@ -912,7 +964,7 @@ extern "C" int petmh_synth(petmh_t* h, int n_tac, uint64_t seed, const double* m
     sp.truth = h->d_synth_truth; sp.clean = h->d_synth_clean; sp.attempts = h->d_synth_attempts;
     h->n_tac = n_tac;
     SweepParams p = base_params(h);
-    synth_kernel<<<n_tac, 64, SM_STATE + 32 * SLOTS * NT * 4, h->stream>>>(p, sp);
+    synth_kernel<<<n_tac, 64, HOOK_SMEM, h->stream>>>(p, sp);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(h->stream));
     h->have_data = true;

@@ -39,6 +39,31 @@ constexpr int RSTRIDE = PETMH_RSTRIDE;// 20 floats per packed column of a block
 constexpr int NPAIR = RB / 2;         // 9 accumulator pairs per item
 static_assert(RB == 18 && NBLK == 3 && RSTRIDE == 20 && YS == NBLK * RSTRIDE, "eval3 is written for 3 blocks of 18 rows");
 
+// Chebyshev-in-k2a form of the operator (the hot path).  For k2a = k2p R1/DVR
+// (kinetic_model.py:153-154) with k2a t_last in [CHEB_KT_LO, CHEB_KT_HI] and s = (k2a - kmid)/h in [-1, 1]:
+//   exp(-k2a t_f) = e^{-kmid t_f} [ I_0(h t_f) + 2 sum_{d>=1} (-1)^d I_d(h t_f) T_d(s) ]
+// so  conv = M e = A T(s),  A = M C  (54 x D per TAC),  C[f][d] a frame-grid-only table (host-built, fp64).
+// Row block b keeps NCH[b] columns: truncation error of conv <= 5e-8 relative over the whole range on every test
+// reference TAC (tests/test_oracle_cheb.py), i.e. below the fp32 rounding of either form.  With the reference's
+// grid (t_last = 120 min) and k2p = 0.0126 the range is R1/DVR in [0.149, 3.97].  Items outside it (early tuning at
+// scaling 1, extreme ROIs) are evaluated with the exact operator instead (exact_block): per item, "in range ->
+// Chebyshev, else exact", never depending on neighbouring lanes.
+#ifndef PETMH_CHEB_KT_LO
+#define PETMH_CHEB_KT_LO 0.225
+#define PETMH_CHEB_KT_HI 6.0
+#endif
+constexpr double CHEB_KT_LO = PETMH_CHEB_KT_LO, CHEB_KT_HI = PETMH_CHEB_KT_HI;
+constexpr float CHEB_C0 = (float)((CHEB_KT_HI + CHEB_KT_LO) / (CHEB_KT_HI - CHEB_KT_LO));   // s = k2a * inv_h - C0
+constexpr int NCH0 = 6, NCH1 = 8, NCH2 = 12;              // Chebyshev columns per row block (even: the column loop runs in pairs)
+constexpr int NCHMAX = NCH2;
+// Packed layout [block][NCH_b + 1 columns][RSTRIDE] in the ORDER THE KERNEL ADDS THEM: columns 2 .. NCH_b-1 (small
+// terms first, accumulators start at zero), then column 1, column 0, and last the reference TAC itself (times R1).
+// Adding the large terms last keeps the fp32 partial sums small: rms TAC error 3.9e-8 relative (the exact M e form:
+// 4.7e-8; largest-first order: 7.3e-8; tests/test_oracle_cheb.py).
+constexpr int AOFF1 = (NCH0 + 1) * RSTRIDE, AOFF2 = (NCH0 + NCH1 + 2) * RSTRIDE;
+constexpr int APACK = (NCH0 + NCH1 + NCH2 + 3) * RSTRIDE; // 580 floats
+static_assert(NCH0 % 2 == 0 && NCH1 % 2 == 0 && NCH2 % 2 == 0 && NCH0 >= 4, "column loop: pairs after a two-column head");
+
 // Frame-grid-only tables (host-built in fp64, see petmh.cu build_frame_tables):
 // W_fwd / W_back of SURVEY.md A.2 in sparse two-tap form.
 struct FrameTables {
@@ -49,6 +74,9 @@ struct FrameTables {
     double bwa[NT], bwb[NT];
     int klo[NT], khi[NT];            // grid rows k with W_fwd[k, f] != 0 lie in [klo, khi]
     int acol[NCOL];                  // active column -> frame index
+    int nrow[NT];                    // row j of M uses the first nrow[j] active columns
+    float inv_h;                     // 1/h of the Chebyshev range (fp32, as the kernel uses it)
+    double cheb_c[NCOL][12];         // C[active column][d] for exactly that fp32 range (NCHMAX = 12)
     short pack_src[MPACK];           // packed M slot -> (row << 6 | active col) or -1
 };
 
@@ -214,7 +242,8 @@ __device__ __forceinline__ float half_erfc(float z) {
 // ------------------------------------------------------------------------------------
 constexpr int SM_CRS = 0;                                 // double [NGRID]
 constexpr int SM_M = SM_CRS + NGRID * 8;                  // float [MPACK]   packed operator
-constexpr int SM_CR = SM_M + MPACK * 4;                   // float [64]      reference TAC, [60] = k2p
+constexpr int SM_A = SM_M + MPACK * 4;                    // float [APACK]   Chebyshev operator A = M C
+constexpr int SM_CR = SM_A + APACK * 4;                   // float [64]      reference TAC, [60] = k2p, [61] = inv_h
 constexpr int SM_YCC = SM_CR + 64 * 4;                    // float [48][YS]  -(y * cc)
 constexpr int SM_CC = SM_YCC + 48 * YS * 4;               // float [48][YS]  1/(sigma sqrt2)
 constexpr int SM_BAD = SM_CC + 48 * YS * 4;               // uchar [48] (+pad) 1 if any y < 0
@@ -222,7 +251,10 @@ constexpr int SM_P = SM_BAD + 64;                         // double [2][48][48] 
 constexpr int DM_STRIDE = 64;                             // doubles per chain (48 used; index 63 = "no winner" stays in range)
 constexpr int SM_DMOVE = SM_P + 2 * 48 * 48 * 8;          // double [8 warps][2 chains][DM_STRIDE] proposed moves of the block being resolved
 constexpr int SM_STATE = SM_DMOVE + 8 * 2 * DM_STRIDE * 8;// float [ST_WORDS][nthreads] per-thread chain state
-constexpr int K2P_SLOT = 60;
+constexpr int K2P_SLOT = 60, INVH_SLOT = 61;
+// prologue scratch (aliases the chain-state region, which is filled afterwards): fp64 M [54][45]
+constexpr int TMP_BYTES = NT * NCOL * 8;
+static_assert(NCHMAX == 12, "FrameTables::cheb_c is [NCOL][12]");
 
 // ------------------------------------------------------------------------------------
 // Phase A: forward model + reduced log-likelihood for the lane's 3 ROIs (l16, l16+16,
@@ -379,47 +411,122 @@ __device__ __forceinline__ float block_loglik(const u64 (&raw_in)[NPAIR], const 
     return fmaf(-0.34657359027997264f, Si, -(ga + gb));   // -(ln 2)/2 * log2(prod) - Gaussian term
 }
 
-// HOOK = true only in the parity-hook / generator kernels (writes the unclamped TAC to tac_out); the sweep kernel's
-// instance carries no hook code (hot-code size matters: the kernel is sensitive to instruction-cache misses).
-template <int VARIANT, bool HOOK = false>
-__device__ PETMH_EVAL3_INLINE float3 eval3(const int l16, const float d0, const float d1, const float d2, const float a0,
-                                     const float a1, const float a2, float* tac_out) {
+// ------------------------------------------------------------------------------------
+// The exact operator path (cold code): conv = M e with the packed triangle schedule of m_schedule.inc, one item per
+// lane, one row block.  Used for items whose R1/DVR is outside the Chebyshev range, and by the parity hooks.
+// HOOK: also write the block's unclamped TAC to tac_item[NT] when `wr`.
+// ------------------------------------------------------------------------------------
+template <bool HOOK>
+__device__ __forceinline__ float exact_block(const int roi, const float dv, const float av, const int blk, float* tac_item,
+                                             const bool wr) {
     extern __shared__ __align__(16) unsigned char smem[];
     const float* sM = reinterpret_cast<const float*>(smem + SM_M);
     const float* sCr = reinterpret_cast<const float*>(smem + SM_CR);
     const float k2p = sCr[K2P_SLOT];
-    // rotating per-item registers: slot 0 is the item being processed by the likelihood loop
-    float na0, na1, na2, coef0, coef1, coef2, r10 = a0, r11 = a1, r12 = a2;
-    float v0 = 0.f, v1 = 0.f, v2 = 0.f;   // per-item log-likelihood, accumulated over the row blocks
-    {
-        const float k20 = k2p * a0, k21 = k2p * a1, k22 = k2p * a2;   // kinetic_model.py:153
-        const float k2a0 = k20 / d0, k2a1 = k21 / d1, k2a2 = k22 / d2; // :154
-        coef0 = fmaf(-a0, k2a0, k20);                                   // (k2 - R1*k2a), :157
-        coef1 = fmaf(-a1, k2a1, k21);
-        coef2 = fmaf(-a2, k2a2, k22);
-        na0 = k2a0 * -1.4426950408889634f;                              // exp(-k2a t) = 2^(na t)
-        na1 = k2a1 * -1.4426950408889634f;
-        na2 = k2a2 * -1.4426950408889634f;
+    const float k2 = k2p * av, k2a = k2 / dv;                    // kinetic_model.py:153-154
+    const float coef = fmaf(-av, k2a, k2);                       // (k2 - R1*k2a), :157
+    const float na = k2a * -1.4426950408889634f;                 // exp(-k2a t) = 2^(na t)
+    const float* yrow0 = reinterpret_cast<const float*>(smem + SM_YCC) + roi * YS;
+    const float* crow0 = reinterpret_cast<const float*>(smem + SM_CC) + roi * YS;
+    const u64 coefd = pack2(coef, coef), r1d = pack2(av, av);
+    const float4* Mp = reinterpret_cast<const float4*>(sM + (blk == 0 ? 0 : (blk == 1 ? 220 : 780)));   // PETMH_MOFF
+    u64 acc[NPAIR];
+#pragma unroll
+    for (int pq = 0; pq < NPAIR; pq++) acc[pq] = 0ull;
+    // Column c touches only row pairs >= z(c) (the operator is a triangle): phase z runs the columns
+    // [cend[z-1], cend[z]) over pairs z..8 (tools/gen_schedule.py).
+#define PETMH_COL1(ZP)                                                                                           \
+    {                                                                                                            \
+        const float e_ = ex2_approx(na * c_tcol[c]);                                                             \
+        const u64 ed_ = pack2(e_, e_);                                                                           \
+        if ((ZP) <= 1) { const float4 m = Mp[0]; if ((ZP) <= 0) ffma2(acc[0], pack2(m.x, m.y), ed_); ffma2(acc[1], pack2(m.z, m.w), ed_); } \
+        if ((ZP) <= 3) { const float4 m = Mp[1]; if ((ZP) <= 2) ffma2(acc[2], pack2(m.x, m.y), ed_); ffma2(acc[3], pack2(m.z, m.w), ed_); } \
+        if ((ZP) <= 5) { const float4 m = Mp[2]; if ((ZP) <= 4) ffma2(acc[4], pack2(m.x, m.y), ed_); ffma2(acc[5], pack2(m.z, m.w), ed_); } \
+        if ((ZP) <= 7) { const float4 m = Mp[3]; if ((ZP) <= 6) ffma2(acc[6], pack2(m.x, m.y), ed_); ffma2(acc[7], pack2(m.z, m.w), ed_); } \
+        { const float2 m = *reinterpret_cast<const float2*>(Mp + 4); ffma2(acc[8], pack2(m.x, m.y), ed_); }       \
     }
-    int rowoff0 = l16 * YS, rowoff1 = (l16 + 16) * YS, rowoff2 = (l16 + 32) * YS;   // ROI rows of ycc / cc
+#define PETMH_PHASE1(ZP)                                                                                         \
+    {                                                                                                            \
+        const int ce_ = c_cend[blk][ZP];                                                                          \
+        _Pragma("unroll 1") for (int c = (ZP) == 0 ? 0 : c_cend[blk][(ZP) == 0 ? 0 : (ZP) - 1]; c < ce_; c++, Mp += RSTRIDE / 4) PETMH_COL1(ZP) \
+    }
+    PETMH_PHASE1(0) PETMH_PHASE1(1) PETMH_PHASE1(2) PETMH_PHASE1(3) PETMH_PHASE1(4)
+    PETMH_PHASE1(5) PETMH_PHASE1(6) PETMH_PHASE1(7) PETMH_PHASE1(8)
+#undef PETMH_PHASE1
+#undef PETMH_COL1
+    const float* crb = sCr + blk * RB;
+    u64 raw[NPAIR];
+#pragma unroll
+    for (int pq = 0; pq < NPAIR; pq++) {
+        const float2 c = *reinterpret_cast<const float2*>(crb + 2 * pq);
+        raw[pq] = ffma2r(acc[pq], coefd, fmul2(pack2(c.x, c.y), r1d));   // R1 c_r + coef conv (kinetic_model.py:157)
+    }
+    if (HOOK && wr) {
+#pragma unroll
+        for (int pq = 0; pq < NPAIR; pq++) {
+            float c0, c1;
+            unpack2(raw[pq], c0, c1);
+            tac_item[blk * RB + 2 * pq] = c0;
+            tac_item[blk * RB + 2 * pq + 1] = c1;
+        }
+    }
+    return block_loglik(raw, crow0 + blk * RSTRIDE, yrow0 + blk * RSTRIDE);
+}
+// all three row blocks of one item, summed in block order from 0 (as every path accumulates them)
+template <bool HOOK>
+__device__ __noinline__ float exact_item(const int roi, const float dv, const float av, float* tac_item, const bool wr) {
+    float v = 0.f;
+#pragma unroll 1
+    for (int blk = 0; blk < NBLK; blk++) v += exact_block<HOOK>(roi, dv, av, blk, tac_item, wr);
+    return v;
+}
+
+// Per-item scalars of the Chebyshev form: coef = k2 - R1 k2a, s in [-1, 1] iff the item is in range.
+__device__ __forceinline__ void cheb_item(const float k2p, const float inv_h, const float dv, const float av, float& coef,
+                                          float& s, bool& oob) {
+    const float k2 = k2p * av, k2a = k2 / dv;                    // kinetic_model.py:153-154
+    coef = fmaf(-av, k2a, k2);                                   // (k2 - R1*k2a), :157
+    s = fmaf(k2a, inv_h, -CHEB_C0);
+    oob = !(fabsf(s) <= 1.0f);                                   // NaN -> exact path (which rejects it like the reference)
+}
+
+// HOOK = true only in the parity-hook / generator kernels (writes the unclamped TAC to tac_out); the sweep kernel's
+// instance carries no hook code (hot-code size matters: the kernel is sensitive to instruction-cache misses).
+//
+// TAC_j = R1 c_r[j] + sum_d A[j][d] (coef T_d(s)): the accumulators start at R1 c_r, the recurrence
+// T'_{d+1} = 2 s T'_d - T'_{d-1} runs on coef-scaled values (T'_{-1} = coef s, T'_0 = coef), so the column loop
+// leaves the unclamped TAC itself -- 9 FFMA2 per column and item, every column full, no exponentials.
+template <int VARIANT, bool HOOK = false>
+__device__ PETMH_EVAL3_INLINE float3 eval3(const int l16, const float d0, const float d1, const float d2, const float a0,
+                                     const float a1, const float a2, float* tac_out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const float* sA = reinterpret_cast<const float*>(smem + SM_A);
+    const float* sCr = reinterpret_cast<const float*>(smem + SM_CR);
+    float coef0, coef1, coef2, s0, s1, s2;
+    bool oob0, oob1, oob2;
+    {
+        const float k2p = sCr[K2P_SLOT], inv_h = sCr[INVH_SLOT];
+        cheb_item(k2p, inv_h, d0, a0, coef0, s0, oob0);
+        cheb_item(k2p, inv_h, d1, a1, coef1, s1, oob1);
+        cheb_item(k2p, inv_h, d2, a2, coef2, s2, oob2);
+    }
+    const float ts0 = s0 + s0, ts1 = s1 + s1, ts2 = s2 + s2;
+    const float cs0 = __fmul_rn(coef0, s0), cs1 = __fmul_rn(coef1, s1), cs2 = __fmul_rn(coef2, s2);
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f;   // per-item log-likelihood, accumulated over the row blocks
+    const int rowoff0 = l16 * YS, rowoff1 = (l16 + 16) * YS, rowoff2 = (l16 + 32) * YS;   // ROI rows of ycc / cc
     const float* sYcc = reinterpret_cast<const float*>(smem + SM_YCC);
     const float* sCc = reinterpret_cast<const float*>(smem + SM_CC);
 
 #pragma unroll 1
     for (int blk = 0; blk < NBLK; blk++) {
-        const float4* Mp = reinterpret_cast<const float4*>(sM + (blk == 0 ? 0 : (blk == 1 ? 220 : 780)));   // PETMH_MOFF
+        const float4* Ap = reinterpret_cast<const float4*>(sA + (blk == 0 ? 0 : (blk == 1 ? AOFF1 : AOFF2)));
+        const int n0 = blk == 0 ? NCH0 : (blk == 1 ? NCH1 : NCH2);
         u64 acc0[NPAIR], acc1[NPAIR], acc2[NPAIR];
 #pragma unroll
         for (int p = 0; p < NPAIR; p++) acc0[p] = acc1[p] = acc2[p] = 0ull;
-        // ---- conv rows of this block: acc += M[:, c] * e_c over the block's active columns ----
-        // Column c touches only row pairs >= z(c) (the operator is a triangle): phase z runs the columns
-        // [cend[z-1], cend[z]) over pairs z..8.  Phase 0 (the bulk) is software-pipelined with two
-        // register buffers (ping-pong, no copies); FFMA2 takes the exponential as scalar-broadcast operand.
-#define PETMH_EXPS(E, c_)                                                                                        \
-    {                                                                                                            \
-        const float tc_ = c_tcol[c_];                                                                            \
-        E##0 = ex2_approx(na0 * tc_); E##1 = ex2_approx(na1 * tc_); E##2 = ex2_approx(na2 * tc_);                \
-    }
+        // ---- acc += A[:, d] * T'_d: columns 2 .. n0-1 (recurrence), then 1, 0 and the c_r column (times R1);
+        // software-pipelined with two register buffers (ping-pong, no copies); FFMA2 takes the per-item scalar as
+        // broadcast operand.
 #define PETMH_PAIR(E, pq, m01)                                                                                   \
     { ffma2(acc0[pq], m01, pack2(E##0, E##0)); ffma2(acc1[pq], m01, pack2(E##1, E##1)); ffma2(acc2[pq], m01, pack2(E##2, E##2)); }
 #define PETMH_CH(E, v, m)                                                                                        \
@@ -429,78 +536,49 @@ __device__ PETMH_EVAL3_INLINE float3 eval3(const int l16, const float d0, const 
 #define PETMH_FULLCOL(B, E)                                                                                      \
     { PETMH_CH(E, 0, B##0) PETMH_CH(E, 1, B##1) PETMH_CH(E, 2, B##2) PETMH_CH(E, 3, B##3) PETMH_PAIR(E, 8, pack2((B##4).x, (B##4).y)) }
         {
-            const int n0 = c_cend[blk][PETMH_TRIANGLE ? 0 : 8];
             float4 ma0, ma1, ma2, ma3, mb0, mb1, mb2, mb3;
             float2 ma4, mb4;
-            float ea0, ea1, ea2, eb0, eb1, eb2;
-            PETMH_LOADCOL(ma, Mp)
-            PETMH_EXPS(ea, 0)
-            int c = 0;
-#pragma unroll 2
-            for (; c + 1 < n0; c += 2) {
-                PETMH_LOADCOL(mb, Mp + (RSTRIDE / 4))
-                PETMH_EXPS(eb, c + 1)
-                PETMH_FULLCOL(ma, ea)
-                PETMH_LOADCOL(ma, Mp + 2 * (RSTRIDE / 4))   // (reads / exponentials past the block's last column are harmless)
-                PETMH_EXPS(ea, c + 2)
-                PETMH_FULLCOL(mb, eb)
-                Mp += 2 * (RSTRIDE / 4);
+            // (x, y) = (T'_c, T'_{c-1}) entering the pair of columns c, c + 1
+            float y0 = cs0, y1 = cs1, y2 = cs2;
+            float x0 = fmaf(ts0, cs0, -coef0), x1 = fmaf(ts1, cs1, -coef1), x2 = fmaf(ts2, cs2, -coef2);
+            PETMH_LOADCOL(ma, Ap)
+#pragma unroll 1
+            for (int c = 2; c < n0; c += 2) {
+                PETMH_LOADCOL(mb, Ap + (RSTRIDE / 4))
+                y0 = fmaf(ts0, x0, -y0); y1 = fmaf(ts1, x1, -y1); y2 = fmaf(ts2, x2, -y2);   // T'_{c+1}
+                PETMH_FULLCOL(ma, x)
+                PETMH_LOADCOL(ma, Ap + 2 * (RSTRIDE / 4))
+                x0 = fmaf(ts0, y0, -x0); x1 = fmaf(ts1, y1, -x1); x2 = fmaf(ts2, y2, -x2);   // T'_{c+2} (unused after the last pair)
+                PETMH_FULLCOL(mb, y)
+                Ap += 2 * (RSTRIDE / 4);
             }
-            if (c < n0) {
-                PETMH_FULLCOL(ma, ea)
-                Mp += RSTRIDE / 4;
-            }
+            PETMH_LOADCOL(mb, Ap + (RSTRIDE / 4))
+            PETMH_FULLCOL(ma, cs)                        // column 1: T'_1 = coef s
+            PETMH_LOADCOL(ma, Ap + 2 * (RSTRIDE / 4))
+            PETMH_FULLCOL(mb, coef)                      // column 0: T'_0 = coef
+            PETMH_FULLCOL(ma, a)                         // R1 c_r (kinetic_model.py:157)
         }
-        // partial columns: pairs z..8 only
-#define PETMH_PHASE(ZP)                                                                                           \
-    {                                                                                                            \
-        const int ce_ = c_cend[blk][ZP];                                                                          \
-        _Pragma("unroll 1") for (int c = c_cend[blk][(ZP) - 1]; c < ce_; c++, Mp += RSTRIDE / 4) {                \
-            float ep0, ep1, ep2; PETMH_EXPS(ep, c)                                                                                        \
-            if ((ZP) <= 1) { const float4 m = Mp[0]; if ((ZP) <= 0) PETMH_PAIR(ep, 0, pack2(m.x, m.y)) PETMH_PAIR(ep, 1, pack2(m.z, m.w)) } \
-            if ((ZP) <= 3) { const float4 m = Mp[1]; if ((ZP) <= 2) PETMH_PAIR(ep, 2, pack2(m.x, m.y)) PETMH_PAIR(ep, 3, pack2(m.z, m.w)) } \
-            if ((ZP) <= 5) { const float4 m = Mp[2]; if ((ZP) <= 4) PETMH_PAIR(ep, 4, pack2(m.x, m.y)) PETMH_PAIR(ep, 5, pack2(m.z, m.w)) } \
-            if ((ZP) <= 7) { const float4 m = Mp[3]; if ((ZP) <= 6) PETMH_PAIR(ep, 6, pack2(m.x, m.y)) PETMH_PAIR(ep, 7, pack2(m.z, m.w)) } \
-            { const float2 m = *reinterpret_cast<const float2*>(Mp + 4); PETMH_PAIR(ep, 8, pack2(m.x, m.y)) }        \
-        }                                                                                                        \
-    }
-#if PETMH_TRIANGLE
-        PETMH_PHASE(1) PETMH_PHASE(2) PETMH_PHASE(3) PETMH_PHASE(4) PETMH_PHASE(5) PETMH_PHASE(6) PETMH_PHASE(7) PETMH_PHASE(8)
-#endif
-#undef PETMH_PHASE
 #undef PETMH_FULLCOL
 #undef PETMH_LOADCOL
 #undef PETMH_CH
 #undef PETMH_PAIR
-#undef PETMH_EXPS
-        // ---- likelihood of the block's 18 frames, one item per iteration (registers rotate) ----
-        const float* crb = sCr + blk * RB;
+        // ---- likelihood of the block's 18 frames, one item per iteration ----
 #pragma unroll 1
         for (int it = 0; it < K; it++) {   // (fully unrolling this loop was measured slower: code size)
-#define PETMH_SEL(x0, x1, x2) (it == 0 ? (x0) : (it == 1 ? (x1) : (x2)))
-            const int rowoff = PETMH_SEL(rowoff0, rowoff1, rowoff2);
-            const float coefi = PETMH_SEL(coef0, coef1, coef2), r1i = PETMH_SEL(r10, r11, r12);
-#undef PETMH_SEL
+            const int rowoff = it == 0 ? rowoff0 : (it == 1 ? rowoff1 : rowoff2);
             const float* yrow = sYcc + rowoff + blk * RSTRIDE;
             const float* crow = sCc + rowoff + blk * RSTRIDE;
-            const u64 coefd = pack2(coefi, coefi), r1d = pack2(r1i, r1i);
-            // unclamped TAC of the item's 18 frames: R1 c_r + coef conv (kinetic_model.py:157).  `it` is uniform:
-            // one short branch per item picks the accumulator set (no register rotation, no per-pair selects)
+            // `it` is uniform: one short branch per item picks the accumulator set = the item's unclamped TAC pairs
             u64 raw[NPAIR];
-#pragma unroll
-            for (int pq = 0; pq < NPAIR; pq++) {
-                const float2 c = *reinterpret_cast<const float2*>(crb + 2 * pq);
-                raw[pq] = fmul2(pack2(c.x, c.y), r1d);
-            }
             if (it == 0) {
 #pragma unroll
-                for (int pq = 0; pq < NPAIR; pq++) raw[pq] = ffma2r(acc0[pq], coefd, raw[pq]);
+                for (int pq = 0; pq < NPAIR; pq++) raw[pq] = acc0[pq];
             } else if (it == 1) {
 #pragma unroll
-                for (int pq = 0; pq < NPAIR; pq++) raw[pq] = ffma2r(acc1[pq], coefd, raw[pq]);
+                for (int pq = 0; pq < NPAIR; pq++) raw[pq] = acc1[pq];
             } else {
 #pragma unroll
-                for (int pq = 0; pq < NPAIR; pq++) raw[pq] = ffma2r(acc2[pq], coefd, raw[pq]);
+                for (int pq = 0; pq < NPAIR; pq++) raw[pq] = acc2[pq];
             }
             if (HOOK) {   // parity hook only: the unclamped TAC
 #pragma unroll
@@ -517,70 +595,84 @@ __device__ PETMH_EVAL3_INLINE float3 eval3(const int l16, const float d0, const 
             v2 += it == 2 ? vi : 0.f;
         }
     }
+    // ---- items outside the Chebyshev range: the exact operator, slot by slot (warp-converged calls: block_loglik
+    // votes with the full mask), the result taken by the out-of-range lanes only ----
+    if (__any_sync(0xffffffffu, oob0 || oob1 || oob2)) {
+#pragma unroll 1
+        for (int sl = 0; sl < SLOTS; sl++) {
+            const bool ob = sl == 0 ? oob0 : (sl == 1 ? oob1 : oob2);
+            if (!__any_sync(0xffffffffu, ob)) continue;
+            const float dv = sl == 0 ? d0 : (sl == 1 ? d1 : d2), av = sl == 0 ? a0 : (sl == 1 ? a1 : a2);
+            const float e = exact_item<HOOK>(l16 + 16 * sl, dv, av, HOOK ? tac_out + sl * NT : nullptr, ob);
+            if (ob) {
+                if (sl == 0) v0 = e; else if (sl == 1) v1 = e; else v2 = e;
+            }
+        }
+    }
     const unsigned char* bad = smem + SM_BAD;
     return make_float3(bad[l16] ? -INFINITY : v0, bad[l16 + 16] ? -INFINITY : v1, bad[l16 + 32] ? -INFINITY : v2);
 }
 
 // One item per lane (the "wide" small-job paths: the three ROI slots of a lane -- and, in the nine-warp variant, the
 // three row blocks of a slot -- are evaluated by different warps).  Per item the operations and their order are exactly
-// those of eval3, so the results are bit-identical.  eval1_block = one row block's share of the log-likelihood.
-__device__ __forceinline__ float eval1_block(const int roi, const float dv, const float av, const int blk) {
+// those of eval3, so the results are bit-identical.  cheb_block = one row block's share of the log-likelihood.
+__device__ __forceinline__ float cheb_block(const int roi, const float av, const float coef, const float s, const int blk) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const float* sM = reinterpret_cast<const float*>(smem + SM_M);
-    const float* sCr = reinterpret_cast<const float*>(smem + SM_CR);
-    const float k2p = sCr[K2P_SLOT];
-    const float k2 = k2p * av, k2a = k2 / dv;
-    const float coef = fmaf(-av, k2a, k2);
-    const float na = k2a * -1.4426950408889634f;
-    const float* yrow0 = reinterpret_cast<const float*>(smem + SM_YCC) + roi * YS;
-    const float* crow0 = reinterpret_cast<const float*>(smem + SM_CC) + roi * YS;
-    const u64 coefd = pack2(coef, coef), r1d = pack2(av, av);
-    {
-        const float4* Mp = reinterpret_cast<const float4*>(sM + (blk == 0 ? 0 : (blk == 1 ? 220 : 780)));   // PETMH_MOFF
-        u64 acc[NPAIR];
+    const float* sA = reinterpret_cast<const float*>(smem + SM_A);
+    const float4* Ap = reinterpret_cast<const float4*>(sA + (blk == 0 ? 0 : (blk == 1 ? AOFF1 : AOFF2)));
+    const int n0 = blk == 0 ? NCH0 : (blk == 1 ? NCH1 : NCH2);
+    u64 acc[NPAIR];
 #pragma unroll
-        for (int pq = 0; pq < NPAIR; pq++) acc[pq] = 0ull;
-#define PETMH_COL1(ZP)                                                                                           \
-    {                                                                                                            \
-        const float e_ = ex2_approx(na * c_tcol[c]);                                                             \
-        const u64 ed_ = pack2(e_, e_);                                                                           \
-        if ((ZP) <= 1) { const float4 m = Mp[0]; if ((ZP) <= 0) ffma2(acc[0], pack2(m.x, m.y), ed_); ffma2(acc[1], pack2(m.z, m.w), ed_); } \
-        if ((ZP) <= 3) { const float4 m = Mp[1]; if ((ZP) <= 2) ffma2(acc[2], pack2(m.x, m.y), ed_); ffma2(acc[3], pack2(m.z, m.w), ed_); } \
-        if ((ZP) <= 5) { const float4 m = Mp[2]; if ((ZP) <= 4) ffma2(acc[4], pack2(m.x, m.y), ed_); ffma2(acc[5], pack2(m.z, m.w), ed_); } \
-        if ((ZP) <= 7) { const float4 m = Mp[3]; if ((ZP) <= 6) ffma2(acc[6], pack2(m.x, m.y), ed_); ffma2(acc[7], pack2(m.z, m.w), ed_); } \
-        { const float2 m = *reinterpret_cast<const float2*>(Mp + 4); ffma2(acc[8], pack2(m.x, m.y), ed_); }       \
-    }
-#define PETMH_PHASE1(ZP, UNR)                                                                                    \
-    {                                                                                                            \
-        const int ce_ = c_cend[blk][ZP];                                                                          \
-        _Pragma(UNR) for (int c = (ZP) == 0 ? 0 : c_cend[blk][(ZP) == 0 ? 0 : (ZP) - 1]; c < ce_; c++, Mp += RSTRIDE / 4) PETMH_COL1(ZP) \
-    }
-        PETMH_PHASE1(0, "unroll 4")
-        PETMH_PHASE1(1, "unroll 1") PETMH_PHASE1(2, "unroll 1") PETMH_PHASE1(3, "unroll 1") PETMH_PHASE1(4, "unroll 1")
-        PETMH_PHASE1(5, "unroll 1") PETMH_PHASE1(6, "unroll 1") PETMH_PHASE1(7, "unroll 1") PETMH_PHASE1(8, "unroll 1")
-#undef PETMH_PHASE1
-#undef PETMH_COL1
-        const float* crb = sCr + blk * RB;
-        const float* yrow = yrow0 + blk * RSTRIDE;
-        const float* crow = crow0 + blk * RSTRIDE;
-        u64 raw[NPAIR];
+    for (int p = 0; p < NPAIR; p++) acc[p] = 0ull;
+    const float ts = s + s, cs = __fmul_rn(coef, s);
+    float tp = coef, tc = cs;                       // T'_{c-2}, T'_{c-1}
+#pragma unroll 1
+    for (int c = 2; c < n0 + 3; c++, Ap += RSTRIDE / 4) {
+        // columns 2 .. n0-1 by the recurrence, then column 1 (coef s), column 0 (coef), the c_r column (R1)
+        float w;
+        if (c < n0) { w = fmaf(ts, tc, -tp); tp = tc; tc = w; }
+        else w = c == n0 ? cs : (c == n0 + 1 ? coef : av);
+        const u64 wd = pack2(w, w);
 #pragma unroll
-        for (int pq = 0; pq < NPAIR; pq++) {
-            const float2 c = *reinterpret_cast<const float2*>(crb + 2 * pq);
-            raw[pq] = ffma2r(acc[pq], coefd, fmul2(pack2(c.x, c.y), r1d));
+        for (int v = 0; v < 4; v++) {
+            const float4 m = Ap[v];
+            ffma2(acc[2 * v], pack2(m.x, m.y), wd);
+            ffma2(acc[2 * v + 1], pack2(m.z, m.w), wd);
         }
-        return block_loglik(raw, crow, yrow);
+        const float2 m = *reinterpret_cast<const float2*>(Ap + 4);
+        ffma2(acc[8], pack2(m.x, m.y), wd);
     }
+    const float* yrow = reinterpret_cast<const float*>(smem + SM_YCC) + roi * YS + blk * RSTRIDE;
+    const float* crow = reinterpret_cast<const float*>(smem + SM_CC) + roi * YS + blk * RSTRIDE;
+    return block_loglik(acc, crow, yrow);
 }
 __device__ __noinline__ float eval1(const int roi, const float dv, const float av) {
     extern __shared__ __align__(16) unsigned char smem[];
+    const float* sCr = reinterpret_cast<const float*>(smem + SM_CR);
+    float coef, s;
+    bool oob;
+    cheb_item(sCr[K2P_SLOT], sCr[INVH_SLOT], dv, av, coef, s, oob);
     float v = 0.f;
 #pragma unroll 1
-    for (int blk = 0; blk < NBLK; blk++) v += eval1_block(roi, dv, av, blk);
+    for (int blk = 0; blk < NBLK; blk++) v += cheb_block(roi, av, coef, s, blk);
+    if (__any_sync(0xffffffffu, oob)) {
+        const float e = exact_item<false>(roi, dv, av, nullptr, false);
+        if (oob) v = e;
+    }
     return (smem + SM_BAD)[roi] ? -INFINITY : v;
 }
 __device__ __noinline__ float eval1_blk(const int roi, const float dv, const float av, const int blk) {
-    return eval1_block(roi, dv, av, blk);
+    extern __shared__ __align__(16) unsigned char smem[];
+    const float* sCr = reinterpret_cast<const float*>(smem + SM_CR);
+    float coef, s;
+    bool oob;
+    cheb_item(sCr[K2P_SLOT], sCr[INVH_SLOT], dv, av, coef, s, oob);
+    float v = cheb_block(roi, av, coef, s, blk);
+    if (__any_sync(0xffffffffu, oob)) {
+        const float e = exact_block<false>(roi, dv, av, blk, nullptr, false);
+        if (oob) v = e;
+    }
+    return v;
 }
 
 // ------------------------------------------------------------------------------------
@@ -612,19 +704,39 @@ __device__ __forceinline__ double m_entry(const FrameTables* ft, const double* c
     }
     return tot * ft->dx;
 }
-__device__ __forceinline__ void build_M_packed(const FrameTables* ft, const double* crs, float* Mp, int tid,
-                                               int nthr) {
+// Packed exact operator M (fp32, for exact_block) and the Chebyshev operator A = M C (fp32) from one fp64 M.
+// tmp: TMP_BYTES of scratch (fp64 M [NT][NCOL] by active column).
+__device__ __forceinline__ void build_operators(const FrameTables* ft, const double* crs, const double* __restrict__ cref,
+                                                float* Mp, float* Ap, double* tM, int tid, int nthr) {
+    for (int idx = tid; idx < NT * NCOL; idx += nthr) {
+        const int j = idx / NCOL, c = idx - j * NCOL;
+        tM[idx] = c < ft->nrow[j] ? m_entry(ft, crs, j, ft->acol[c]) : 0.0;
+    }
+    __syncthreads();
     for (int idx = tid; idx < MPACK; idx += nthr) {
         const int src = ft->pack_src[idx];
-        float v = 0.f;
-        if (src >= 0) v = (float)m_entry(ft, crs, src >> 6, ft->acol[src & 63]);
-        Mp[idx] = v;
+        Mp[idx] = src >= 0 ? (float)tM[(src >> 6) * NCOL + (src & 63)] : 0.f;
+    }
+    for (int idx = tid; idx < APACK; idx += nthr) {
+        const int col = idx / RSTRIDE, r = idx - col * RSTRIDE;
+        const int blk = col < NCH0 + 1 ? 0 : (col < NCH0 + NCH1 + 2 ? 1 : 2);
+        const int pc = col - (blk == 0 ? 0 : (blk == 1 ? NCH0 + 1 : NCH0 + NCH1 + 2));   // position in the block's add order
+        const int n0 = blk == 0 ? NCH0 : (blk == 1 ? NCH1 : NCH2);
+        const int d = pc < n0 - 2 ? pc + 2 : (pc == n0 - 2 ? 1 : (pc == n0 - 1 ? 0 : -1));  // -1: the c_r column
+        double v = 0.0;
+        if (r < RB) {
+            const int j = blk * RB + r, n = ft->nrow[j];
+            if (d < 0) v = cref[j];
+            else for (int c = 0; c < n; c++) v = fma(tM[j * NCOL + c], ft->cheb_c[c][d], v);
+        }
+        Ap[idx] = (float)v;
     }
 }
 
 __device__ __forceinline__ void load_tac_image(const SweepParams& p, int tac, unsigned char* smem, int tid, int nthr) {
     double* sCrs = reinterpret_cast<double*>(smem + SM_CRS);
     float* sM = reinterpret_cast<float*>(smem + SM_M);
+    float* sA = reinterpret_cast<float*>(smem + SM_A);
     float* sCr = reinterpret_cast<float*>(smem + SM_CR);
     float* sYcc = reinterpret_cast<float*>(smem + SM_YCC);
     float* sCc = reinterpret_cast<float*>(smem + SM_CC);
@@ -634,10 +746,12 @@ __device__ __forceinline__ void load_tac_image(const SweepParams& p, int tac, un
         for (int i = tid; i < 2 * 48 * 48; i += nthr) sPd[i] = p.P[i];
     }
     const double* cref = p.cref + (size_t)tac * NT;
+    const float k2p = p.k2p[tac], inv_h = p.ft->inv_h;
     build_crs(p.ft, cref, sCrs, tid, nthr);
-    for (int i = tid; i < 64; i += nthr) sCr[i] = i < NT ? (float)cref[i] : (i == K2P_SLOT ? p.k2p[tac] : 0.f);
+    for (int i = tid; i < 64; i += nthr)
+        sCr[i] = i < NT ? (float)cref[i] : (i == K2P_SLOT ? k2p : (i == INVH_SLOT ? inv_h : 0.f));
     __syncthreads();
-    build_M_packed(p.ft, sCrs, sM, tid, nthr);
+    build_operators(p.ft, sCrs, cref, sM, sA, reinterpret_cast<double*>(smem + SM_STATE), tid, nthr);
     const float* y = p.y + (size_t)tac * NROI * NT;
     int any_neg = 0;
     for (int i = tid; i < NROI * YS; i += nthr) {   // layout [roi][block][RSTRIDE], RB frames used
@@ -1061,6 +1175,22 @@ __global__ void operator_kernel(const SweepParams p, int tac, double* m_out /*[5
     build_crs(p.ft, p.cref + (size_t)tac * NT, crs, threadIdx.x, blockDim.x);
     __syncthreads();
     for (int idx = threadIdx.x; idx < NT * NT; idx += blockDim.x) m_out[idx] = m_entry(p.ft, crs, idx / NT, idx % NT);
+}
+
+// parity hook: the per-TAC Chebyshev operator A (fp32, [3 row blocks][columns][RSTRIDE]) exactly as the sweep kernel's
+// prologue builds it
+__global__ void cheb_operator_kernel(const SweepParams p, int tac, float* a_out /*[(NCH0+NCH1+NCH2)*RSTRIDE], natural order [block][d][RSTRIDE]*/) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    load_tac_image(p, tac, smem, threadIdx.x, blockDim.x);
+    const float* sA = reinterpret_cast<const float*>(smem + SM_A);
+    for (int i = threadIdx.x; i < (NCH0 + NCH1 + NCH2) * RSTRIDE; i += blockDim.x) {
+        const int col = i / RSTRIDE, r = i - col * RSTRIDE;
+        const int blk = col < NCH0 ? 0 : (col < NCH0 + NCH1 ? 1 : 2);
+        const int d = col - (blk == 0 ? 0 : (blk == 1 ? NCH0 : NCH0 + NCH1));
+        const int n0 = blk == 0 ? NCH0 : (blk == 1 ? NCH1 : NCH2);
+        const int pc = d >= 2 ? d - 2 : (d == 1 ? n0 - 2 : n0 - 1);
+        a_out[i] = sA[(blk == 0 ? 0 : (blk == 1 ? AOFF1 : AOFF2)) + pc * RSTRIDE + r];
+    }
 }
 
 __global__ void philox_kernel(unsigned long long seed, unsigned long long gid, uint32_t sweep, uint32_t block,

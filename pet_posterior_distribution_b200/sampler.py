@@ -157,6 +157,19 @@ class MHSampler:
         self._ck(_lib.lib.petmh_get_operator(self._h, int(tac), _d(m)))
         return m
 
+    def cheb_operator(self, tac):
+        """The Chebyshev form of the operator as the sweep kernel uses it: list of three (18, ncols) float32 blocks
+        A_b with conv[18 b : 18 b + 18] = A_b @ T_0..(s), and the k2a range (lo, hi) it is valid on."""
+        a = np.empty(26 * 20, np.float32)
+        nc = (C.c_int * 3)()
+        lo, hi = C.c_double(), C.c_double()
+        self._ck(_lib.lib.petmh_get_cheb_operator(self._h, int(tac), _f(a), nc, C.byref(lo), C.byref(hi)))
+        blocks, off = [], 0
+        for b in range(3):
+            blocks.append(a[off:off + nc[b] * 20].reshape(nc[b], 20)[:, :18].T.copy())
+            off += nc[b] * 20
+        return blocks, (lo.value, hi.value)
+
     def philox_raw(self, chain_gid, sweep, block):
         out = np.empty((N_ROI, 4), np.uint32)
         self._ck(_lib.lib.petmh_philox_raw(self._h, int(chain_gid), int(sweep), int(block),

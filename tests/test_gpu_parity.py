@@ -24,6 +24,28 @@ def test_operator_matches_reference_golden(forward_golden, prior):
         assert ((M != 0) == (g["M"][c] != 0)).all()
 
 
+def test_cheb_operator_matches_oracle(forward_golden, prior):
+    """The per-TAC Chebyshev operator A = M C built in the kernel prologue (fp64 arithmetic, fp32 storage) equals the
+    numpy restatement to fp32 rounding, for the range the library reports."""
+    from oracle import cheb
+    from pet_posterior_distribution_b200 import MHSampler
+    g = forward_golden
+    n = g["c_r"].shape[0]
+    s = MHSampler(n_chains=1, max_tacs=n)
+    s.set_frames(g["t"], g["dt"])
+    s.set_prior(prior["mu_DVR"], prior["Cov_DVR"], prior["mu_R1"], prior["Cov_R1"])
+    s.set_data(np.ones((n, 48, 54)), g["c_r"], g["k2p"], np.ones((48, 54)))
+    for c in range(n):
+        A, (lo, hi) = s.cheb_operator(c)
+        lo0, hi0 = cheb.k2a_range(g["t"])
+        assert abs(lo / lo0 - 1) < 1e-6 and abs(hi / hi0 - 1) < 1e-6      # (the kernel rounds 1/h to fp32)
+        ref = cheb.cheb_operator(g["t"], g["c_r"][c], lo, hi)
+        for b in range(3):
+            assert A[b].shape == ref[b].shape
+            scale = np.abs(ref[b]).max(axis=1, keepdims=True)
+            assert (np.abs(A[b] - ref[b]) <= 1.5e-7 * scale).all()
+
+
 def test_forward_matches_reference_golden(forward_golden, prior):
     """TAC within 1e-5 relative of the live reference's SRTM2.create_activity_curve (fp32 vs fp64)."""
     from pet_posterior_distribution_b200 import MHSampler
