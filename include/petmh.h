@@ -37,6 +37,8 @@ extern "C" {
 #define PETMH_ECUDA (-3)      /* CUDA runtime error */
 #define PETMH_ENOMEM (-4)
 #define PETMH_EGRID (-5)      /* frame grid's operator sparsity differs from the compiled schedule */
+#define PETMH_ESYNTH (-6)     /* petmh_synth: some TACs hit a rejection cap (data bound, attempts[] < 0 marks them) */
+#define PETMH_ESTATE (-7)     /* petmh_set_checkpoint: blob does not match this handle's configuration */
 
 typedef struct petmh_handle petmh_t;
 
@@ -69,6 +71,14 @@ int petmh_set_prior(petmh_t* h, const double* mu_dvr48, const double* cov_dvr48x
  *   sigma_noise[48][54] shared by all TACs       (mcmc.py:96,153) */
 int petmh_set_data(petmh_t* h, int n_tac, const double* y, const double* tac_ref,
                    const double* k2p, const double* sigma_noise);
+/* Global identity of the local TACs and chains, so that Philox streams -- and therefore every draw -- do not depend on
+ * how a job is batched or sharded (replaces nothing in the reference: pm.sample seeds chains by position).  Chain c of
+ * local TAC s draws from stream  gid = tac_gid(s) * chains_per_tac_global + chain_gid0 + c,  tac_gid(s) = tac_gids[s]
+ * if given (e.g. the sample index of mcmc.py:104's loop when some samples are skipped), else cfg.tac_gid0 + s;
+ * chains_per_tac_global = 0 means cfg.n_chains (this handle owns every chain of its TACs).  Splitting the chains of one
+ * TAC over ranks: chain_gid0 = first local chain's global index, chains_per_tac_global = the total. */
+int petmh_set_global_ids(petmh_t* h, int n_tac, const uint64_t* tac_gids, uint64_t chain_gid0,
+                         uint64_t chains_per_tac_global);
 /* same, float32 inputs (bulk path for large batches; pinned memory recommended);
  * sigma_noise may be NULL to keep the previous one. */
 int petmh_set_data_f32(petmh_t* h, int n_tac, const float* y, const float* tac_ref,
@@ -78,11 +88,14 @@ int petmh_set_data_f32(petmh_t* h, int n_tac, const float* y, const float* tac_r
  * Draw, per TAC, DVR / R1 from the handle's priors and the reference TAC from N(mu_tacref, cov_tacref)
  * with positivity rejection (helper_func.py:153-162), forward-simulate, redraw while any clean TAC value is
  * negative (sample_sim_data.py:171-188), add the truncated signal-dependent noise (:205-215) and leave
- * y (= noisy concentration), tac_ref and k2p in the handle as if petmh_set_data had been called. */
+ * y (= noisy concentration), tac_ref and k2p in the handle as if petmh_set_data had been called.
+ * The reference loops until a draw passes; here a vector is redrawn at most 4000 times and the triple at most 1000
+ * times: if any TAC exhausts a cap the call returns PETMH_ESYNTH (the data of the other TACs is valid and bound). */
 int petmh_synth(petmh_t* h, int n_tac, uint64_t seed, const double* mu_tacref54, const double* cov_tacref54x54,
                 double k2p, const double* sigma_noise48x54);
 /* what petmh_synth generated (any pointer may be NULL): dvr_r1[n][96] f32, tac_ref[n][54] f64,
- * tac_clean[n][48][54] f32 and y[n][48][54] f32 in concentration units, attempts[n]. */
+ * tac_clean[n][48][54] f32 and y[n][48][54] f32 in concentration units, attempts[n] (triples drawn; negative
+ * when the TAC hit a rejection cap). */
 int petmh_synth_get(petmh_t* h, float* dvr_r1, double* tac_ref, float* tac_clean, float* y, int* attempts);
 
 /* ---- parity hooks ------------------------------------------------------------------ */
@@ -134,21 +147,52 @@ int petmh_n_stored(const petmh_t* h); /* stored draws per chain so far */
 int petmh_get_chains(petmh_t* h, float* dvr, float* r1);
 /* out[n_tac][96][PETMH_N_STATS] f32: mean, sd, mcse_mean, ess_bulk, ess_tail, r_hat,
  * accept_rate, scaling -- from stored draws when max_draws > 0 (rank-normalised split
- * R-hat / ESS as ArviZ), else from running split-half moments (classic split R-hat,
- * lag-1 (AR(1)) effective sample size; ess_tail = NaN). */
+ * R-hat, bulk / tail ESS and MCSE as ArviZ computes them), else from running split-half moments: the
+ * ess_bulk column then holds a BATCH-MEANS effective sample size (8 batches per half chain; needs >= 4 closed
+ * batches, else NaN), r_hat the CLASSIC (not rank-normalised) split R-hat, ess_tail NaN.  Split halves as ArviZ:
+ * the first and last draws/2 draws of the plan; an odd middle draw counts for neither. */
 int petmh_get_summary(petmh_t* h, float* out);
+/* the remaining pm.summary columns (mcmc.py:181), from the stored draws (max_draws > 0, >= 8 stored):
+ * out[n_tac][96][4] f32 = hdi_3%, hdi_97% (arviz.hdi, hdi_prob 0.94: narrowest interval of the pooled sorted draws),
+ * mcse_sd, ess_sd (arviz _mcse_sd / _ess_sd).  Computed together with petmh_get_summary and cached. */
+int petmh_get_summary_ext(petmh_t* h, float* out);
 /* same, written to a DEVICE buffer (e.g. a slice of an NCCL all-gather buffer) on
  * `stream` (a cudaStream_t, 0 = the handle's). */
 int petmh_summary_device(petmh_t* h, float* d_out, void* stream);
+/* Summaries of state gathered from several handles -- the chains of ONE TAC sampled on several GPUs (SURVEY.md 8e:
+ * "if S < G shard chains"); all pointers are DEVICE pointers on `device`, no handle involved (errors: petmh_last_error(NULL)).
+ *   from_draws:   d_draws[n_tac*n_chains][n_stored][96] f32 (dense), d_nacc / d_scale [n_tac*n_chains][96]
+ *                 -> d_out8[n_tac][96][8] (as petmh_get_summary) and, if not NULL, d_ext4[n_tac][96][4] (as petmh_get_summary_ext)
+ *   from_moments: d_mom[n_tac*n_chains][2][96][5] f32 as the sweep kernel keeps them, d_mu96 = prior means (f64),
+ *                 n_half2 / n_batch2 / batch_len / n_draw_sweeps as petmh_export_summary_inputs reports them.
+ * petmh_export_summary_inputs hands out the handle's own device buffers and counters for such a gather. */
+int petmh_summary_from_draws_device(int device, const float* d_draws, int n_tac, int n_chains, int n_stored,
+                                    const uint32_t* d_nacc, const float* d_scale, int n_draw_sweeps,
+                                    float* d_out8, float* d_ext4, void* stream);
+int petmh_summary_from_moments_device(int device, const float* d_mom, const double* d_mu96, int n_tac, int n_chains,
+                                      const int* n_half2, const int* n_batch2, int batch_len, const uint32_t* d_nacc,
+                                      const float* d_scale, int n_draw_sweeps, float* d_out8, void* stream);
+int petmh_export_summary_inputs(petmh_t* h, void** d_draws, void** d_mom, void** d_nacc, void** d_scale, void** d_mu96,
+                                int* counters8);
 /* out[n_tac][96] f32: cross-chain effective sample size of every coordinate from the stored draws,
  * as the consumer computes it with tfp.mcmc.effective_sample_size(..., cross_chain_dims=-1)
  * (main_script.py:807-810; TFP defaults: lags from the first negative autocorrelation on dropped).
  * Needs max_draws > 0 and >= 2 stored draws; one chain falls back to the single-chain formula. */
 int petmh_get_ess_cross_chain(petmh_t* h, float* out);
 int petmh_get_state(petmh_t* h, float* q /*[n_tac][n_chains][96]*/, float* scale /*same*/);
-/* Resume / warm start: overwrite every chain's position and scaling (either may be NULL),
- * zero the tuning counters and the running moments, and set the sweep counter. */
+/* Warm start: overwrite every chain's position and scaling (either may be NULL), ZERO the tuning counters, the
+ * accepted-move counters and the running moments, and set the sweep counter.  Not a resume -- see
+ * petmh_get_checkpoint / petmh_set_checkpoint for that. */
 int petmh_set_state(petmh_t* h, const float* q, const float* scale, int sweep);
+
+/* Full checkpoint (replaces nothing: the reference can only skip finished samples, mcmc.py:125-128): positions, scalings,
+ * PyMC tune counters, accepted-move counters, running moments, the stored draws and the schedule position, as one
+ * host blob.  After petmh_set_data (same TACs) + petmh_set_checkpoint on a handle with the same n_chains / seed, the
+ * run continues bit for bit as if it had never stopped -- also inside a 100-sweep tuning window.  Returns
+ * PETMH_ESTATE when the blob does not fit the handle. */
+int64_t petmh_checkpoint_bytes(const petmh_t* h);
+int petmh_get_checkpoint(petmh_t* h, void* buf, int64_t nbytes);
+int petmh_set_checkpoint(petmh_t* h, const void* buf, int64_t nbytes);
 
 /* ---- timing / stream ------------------------------------------------------------- */
 int petmh_set_stream(petmh_t* h, void* cuda_stream);

@@ -114,9 +114,12 @@ def mcse_mean(a):
 
 
 def ess_sd(a):
-    """arviz _ess_sd: min of the mean-ESS of the draws and of their squared deviations."""
+    """arviz _ess_sd (arviz/stats/diagnostics.py, 0.12 .. 0.17): ``ary = _split_chains(ary); return min(_ess(ary),
+    _ess(ary ** 2))`` -- the mean-ESS of the draws and of their RAW squares (Stan's original definition; newer
+    `posterior` releases centre first).  Unpinned like the rest of this file: tests/test_pymc_pin.py compares it with
+    az.ess(method="sd") wherever ArviZ is importable."""
     a = np.asarray(a, np.float64)
-    return min(ess_mean(a), ess_mean((a - a.mean()) ** 2))
+    return min(ess_mean(a), ess_mean(a ** 2))
 
 
 def mcse_sd(a):
@@ -124,6 +127,30 @@ def mcse_sd(a):
     a = np.asarray(a, np.float64)
     e = ess_sd(a)
     return a.std(ddof=1) * np.sqrt(np.exp(1) * (1 - 1 / e) ** (e - 1) - 1)
+
+
+def hdi(a, prob=0.94):
+    """arviz.hdi / _hdi (unimodal): narrowest interval holding floor(prob n) + 1 of the pooled sorted draws."""
+    x = np.sort(np.asarray(a, np.float64).ravel())
+    n = x.size
+    inc = int(np.floor(prob * n))
+    w = x[inc:] - x[: n - inc]
+    i = int(np.argmin(w))
+    return x[i], x[i + inc]
+
+
+def batch_means_ess(a, n_batch=8):
+    """The moments-mode estimator of the CUDA library (petmh_diag.cuh), restated: split halves, n_batch batches of
+    B = half // n_batch draws each, sigma2_inf = B * var(batch means about their grand mean),
+    ESS = N var_plus / sigma2_inf.  Not an ArviZ quantity."""
+    a = split_chains(a)
+    m, n = a.shape
+    B = max(1, n // min(n_batch, n))
+    nb = min(n_batch, n // B)
+    bm = a[:, : nb * B].reshape(m, nb, B).mean(axis=2)
+    s2inf = B * ((bm - bm.mean()) ** 2).sum() / (bm.size - 1)
+    var_plus = (n - 1) / n * a.var(axis=1, ddof=1).mean() + a.mean(axis=1).var(ddof=1)
+    return min(m * n * var_plus / s2inf, m * n * np.log10(m * n))
 
 
 def summary_row(a):

@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("PETMH_LIB") or os.path.join(_HERE, "libpetmh.so")   #
 
 N_ROI, N_FRAMES, N_COORD, N_STATS = 48, 54, 96, 8
 STAT_NAMES = ("mean", "sd", "mcse_mean", "ess_bulk", "ess_tail", "r_hat", "accept_rate", "scaling")
+EXT_NAMES = ("hdi_3%", "hdi_97%", "mcse_sd", "ess_sd")
 
 
 class PetmhError(RuntimeError):
@@ -41,6 +42,7 @@ def _load():
         "petmh_set_frames": (C.c_int, [H, dp, dp]),
         "petmh_set_prior": (C.c_int, [H, dp, dp, dp, dp]),
         "petmh_set_data": (C.c_int, [H, C.c_int, dp, dp, dp, dp]),
+        "petmh_set_global_ids": (C.c_int, [H, C.c_int, C.POINTER(C.c_uint64), C.c_uint64, C.c_uint64]),
         "petmh_set_data_f32": (C.c_int, [H, C.c_int, fp, fp, fp, fp]),
         "petmh_synth": (C.c_int, [H, C.c_int, C.c_uint64, dp, dp, C.c_double, dp]),
         "petmh_synth_get": (C.c_int, [H, fp, dp, fp, fp, C.POINTER(C.c_int)]),
@@ -58,10 +60,21 @@ def _load():
         "petmh_n_stored": (C.c_int, [H]),
         "petmh_get_chains": (C.c_int, [H, fp, fp]),
         "petmh_get_summary": (C.c_int, [H, fp]),
+        "petmh_get_summary_ext": (C.c_int, [H, fp]),
         "petmh_summary_device": (C.c_int, [H, C.c_void_p, C.c_void_p]),
+        "petmh_summary_from_draws_device": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                                      C.c_void_p, C.c_void_p, C.c_void_p]),
+        "petmh_summary_from_moments_device": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int),
+                                                        C.POINTER(C.c_int), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                                        C.c_void_p]),
+        "petmh_export_summary_inputs": (C.c_int, [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                                  C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
         "petmh_get_ess_cross_chain": (C.c_int, [H, fp]),
         "petmh_get_state": (C.c_int, [H, fp, fp]),
         "petmh_set_state": (C.c_int, [H, fp, fp, C.c_int]),
+        "petmh_checkpoint_bytes": (C.c_int64, [H]),
+        "petmh_get_checkpoint": (C.c_int, [H, C.c_void_p, C.c_int64]),
+        "petmh_set_checkpoint": (C.c_int, [H, C.c_void_p, C.c_int64]),
         "petmh_set_stream": (C.c_int, [H, C.c_void_p]),
         "petmh_synchronize": (C.c_int, [H]),
         "petmh_last_kernel_ms": (C.c_int, [H, fp, C.POINTER(C.c_int)]),

@@ -29,7 +29,6 @@ struct petmh_handle {
     bool have_frames = false, have_prior = false, have_data = false, have_noise = false;
     FrameTables ft_host{};
     FrameTables* d_ft = nullptr;
-    float tcol[NCOL]{};
     double t[NT]{}, dt[NT]{};
     double mu[2][48]{}, logdet[2]{};
     std::vector<double> P;   // [2][48][48]
@@ -43,14 +42,21 @@ struct petmh_handle {
     double* d_cref = nullptr;
     float* d_k2p = nullptr;
     // state
-    float *d_q = nullptr, *d_scale = nullptr, *d_mom = nullptr, *d_draws = nullptr, *d_mom_first = nullptr;
-    float4* d_momw = nullptr;
+    float *d_q = nullptr, *d_scale = nullptr, *d_mom = nullptr, *d_draws = nullptr;
+    float2* d_momw = nullptr;
     float* d_summary = nullptr;   // [max_tacs][96][8], allocated on first petmh_get_summary
+    float* d_summary_ext = nullptr;   // [max_tacs][96][4]: hdi_3%, hdi_97%, mcse_sd, ess_sd (stored-draw path)
+    int ext_sweep = -1;               // sweep counter the cached extra columns belong to
     // K4 generator
     double cov[2][48 * 48]{};
     double* d_synth_f64 = nullptr;   // factors + means
     float *d_synth_truth = nullptr, *d_synth_clean = nullptr;
     int* d_synth_attempts = nullptr;
+    int* d_synth_capped = nullptr;
+    // global ids of the Philox streams (petmh_set_global_ids)
+    unsigned long long* d_tac_gids = nullptr;
+    bool have_tac_gids = false;
+    unsigned long long chain_gid0 = 0, chain_stride = 0;   // stride 0 = n_chains
     uint8_t* d_cnt = nullptr;
     uint32_t* d_nacc = nullptr;
     // schedule
@@ -58,7 +64,7 @@ struct petmh_handle {
     int sweep = 0;
     bool state_ready = false;     // petmh_reset / petmh_set_state called
     int mom_n[2] = {0, 0};        // draws merged per half
-    int mom_launches[2] = {0, 0}; // launches per half (each contributes nb-1 lag terms)
+    int mom_batches[2] = {0, 0};  // closed batches per half (batch-means ESS of the moments mode)
     // scratch for hooks
     float* d_scratch = nullptr;   // >= 48*54 + 48 + 96 floats
     double* d_scratch64 = nullptr;
@@ -171,7 +177,8 @@ static int build_frame_tables(petmh_t* h, const double* t) {
                         "frame grid not supported: sparsity of the convolution operator (row %d) differs from the "
                         "compiled 54-frame schedule (tools/gen_schedule.py)", j);
     }
-    for (int c = 0; c < NCOL; c++) { ft.acol[c] = acol_c[c]; h->tcol[c] = (float)t[acol_c[c]]; }
+    for (int c = 0; c < NCOL + 3; c++) ft.tcol[c] = 0.f;
+    for (int c = 0; c < NCOL; c++) { ft.acol[c] = acol_c[c]; ft.tcol[c] = (float)t[acol_c[c]]; }
     for (int j = 0; j < NT; j++) ft.nrow[j] = nrow_c[j];
     // Chebyshev table C[f][d] = c_d (-1)^d e^{-kmid t_f} I_d(h t_f) (c_0 = 1, c_d = 2) for the range the kernel's fp32
     // s = k2a * inv_h - C0 maps to [-1, 1]: k2a t_last in [CHEB_KT_LO, CHEB_KT_HI]
@@ -276,9 +283,8 @@ extern "C" int petmh_create(const petmh_cfg* cfg, petmh_t** out) {
     CUC(cudaMalloc(&h->d_scale, NC * 96 * sizeof(float)));
     CUC(cudaMalloc(&h->d_cnt, NC * 96));
     CUC(cudaMalloc(&h->d_nacc, NC * 96 * sizeof(uint32_t)));
-    CUC(cudaMalloc(&h->d_mom, NC * 96 * 6 * sizeof(float)));
-    CUC(cudaMalloc(&h->d_momw, NC * 96 * sizeof(float4)));
-    CUC(cudaMalloc(&h->d_mom_first, NC * 96 * sizeof(float)));
+    CUC(cudaMalloc(&h->d_mom, NC * 96 * 2 * MOMF * sizeof(float)));
+    CUC(cudaMalloc(&h->d_momw, NC * 96 * sizeof(float2)));
     if (cfg->max_draws > 0) CUC(cudaMalloc(&h->d_draws, NC * (size_t)cfg->max_draws * 96 * sizeof(float)));
     CUC(cudaMalloc(&h->d_scratch, (48 * NT + 256) * sizeof(float)));
     CUC(cudaMalloc(&h->d_scratch64, NT * NT * sizeof(double)));
@@ -299,8 +305,8 @@ extern "C" void petmh_destroy(petmh_t* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     void* bufs[] = {h->d_ft, h->d_P, h->d_mu, h->d_cc, h->d_y, h->d_cref, h->d_k2p, h->d_q, h->d_scale,
-                    h->d_cnt, h->d_nacc, h->d_mom, h->d_draws, h->d_scratch, h->d_scratch64, h->d_momw, h->d_mom_first, h->d_summary, h->d_synth_f64, h->d_synth_truth,
-                    h->d_synth_clean, h->d_synth_attempts};
+                    h->d_cnt, h->d_nacc, h->d_mom, h->d_draws, h->d_scratch, h->d_scratch64, h->d_momw, h->d_summary, h->d_summary_ext, h->d_synth_f64, h->d_synth_truth,
+                    h->d_synth_clean, h->d_synth_attempts, h->d_synth_capped, h->d_tac_gids};
     for (void* b : bufs) if (b) cudaFree(b);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -336,15 +342,6 @@ extern "C" int petmh_set_frames(petmh_t* h, const double* t54, const double* dt5
     memcpy(h->t, t54, sizeof h->t);
     memcpy(h->dt, dt54, sizeof h->dt);
     CU(cudaMemcpyAsync(h->d_ft, &h->ft_host, sizeof(FrameTables), cudaMemcpyHostToDevice, h->stream));
-    {   // one frame grid per process (c_tcol is module-wide constant memory)
-        static bool loaded = false;
-        static float loaded_tcol[NCOL];
-        if (loaded && memcmp(loaded_tcol, h->tcol, sizeof loaded_tcol) != 0)
-            return fail(h, PETMH_EINVAL, "a different frame grid is already loaded in this process");
-        CU(cudaMemcpyToSymbolAsync(c_tcol, h->tcol, sizeof h->tcol, 0, cudaMemcpyHostToDevice, h->stream));
-        memcpy(loaded_tcol, h->tcol, sizeof loaded_tcol);
-        loaded = true;
-    }
     CU(cudaStreamSynchronize(h->stream));
     h->have_frames = true;
     return PETMH_OK;
@@ -385,6 +382,26 @@ static int upload_noise(petmh_t* h, const double* sig) {
     CU(cudaMemcpyAsync(h->d_cc, cc.data(), cc.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->have_noise = true;
+    return PETMH_OK;
+}
+
+extern "C" int petmh_set_global_ids(petmh_t* h, int n_tac, const uint64_t* tac_gids, uint64_t chain_gid0,
+                                    uint64_t chains_per_tac_global) {
+    if (!h) return PETMH_EINVAL;
+    if (n_tac < 0 || n_tac > h->cfg.max_tacs) return fail(h, PETMH_EINVAL, "n_tac %d outside [0, max_tacs=%d]", n_tac, h->cfg.max_tacs);
+    if (chains_per_tac_global && chain_gid0 + (uint64_t)h->cfg.n_chains > chains_per_tac_global)
+        return fail(h, PETMH_EINVAL, "chain_gid0 + n_chains exceeds chains_per_tac_global");
+    CU(cudaSetDevice(h->cfg.device));
+    if (tac_gids && n_tac > 0) {
+        if (!h->d_tac_gids) CU(cudaMalloc(&h->d_tac_gids, (size_t)h->cfg.max_tacs * sizeof(unsigned long long)));
+        CU(cudaMemcpyAsync(h->d_tac_gids, tac_gids, (size_t)n_tac * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        h->have_tac_gids = true;
+    } else {
+        h->have_tac_gids = false;
+    }
+    h->chain_gid0 = chain_gid0;
+    h->chain_stride = chains_per_tac_global;
     return PETMH_OK;
 }
 
@@ -465,13 +482,15 @@ static SweepParams base_params(petmh_t* h) {
     p.mom = h->d_mom;
     p.nacc = h->d_nacc;
     p.momw = h->d_momw;
-    p.mom_first = h->d_mom_first;
     p.max_draws = h->cfg.max_draws;
     p.n_tacs = h->n_tac;
     p.n_chains = h->cfg.n_chains;
     p.thin = 1;
     p.seed = h->cfg.seed;
     p.tac_gid0 = h->cfg.tac_gid0;
+    p.tac_gids = h->have_tac_gids ? h->d_tac_gids : nullptr;
+    p.chain_gid0 = h->chain_gid0;
+    p.chain_stride = h->chain_stride ? h->chain_stride : (unsigned long long)h->cfg.n_chains;
     return p;
 }
 
@@ -599,13 +618,14 @@ extern "C" int petmh_reset(petmh_t* h) {
     if (!h->have_prior) return fail(h, PETMH_EINVAL, "petmh_set_prior not called");
     CU(cudaSetDevice(h->cfg.device));
     const size_t NC = (size_t)h->cfg.max_tacs * h->cfg.n_chains;
-    const size_t n = NC * 96 * 6;
+    const size_t n = NC * 96 * 2 * MOMF;
     init_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_q, h->d_scale, h->d_cnt, h->d_nacc, h->d_mom, h->d_mu, NC);
     CU(cudaGetLastError());
     h->sweep = 0;
+    h->ext_sweep = -1;
     h->state_ready = true;
     h->mom_n[0] = h->mom_n[1] = 0;
-    h->mom_launches[0] = h->mom_launches[1] = 0;
+    h->mom_batches[0] = h->mom_batches[1] = 0;
     return PETMH_OK;
 }
 
@@ -616,6 +636,14 @@ extern "C" int petmh_plan(petmh_t* h, int draws, int tune, int thin) {
     h->plan_tune = tune;
     h->plan_thin = thin;
     return PETMH_OK;
+}
+
+// batch-means ESS of the moments mode: every split half (draws / 2 draws) holds up to MOM_NBATCH batches of this length
+// (the estimator is biased high by ~ tau / B for an autocorrelation time tau: long batches matter more than many)
+constexpr int MOM_NBATCH = 8;
+static int moments_batch_len(int plan_draws) {
+    const int n_half = plan_draws / 2;
+    return n_half >= 2 ? std::max(1, n_half / MOM_NBATCH) : 0;
 }
 
 static int threads_per_cta(const petmh_t* h) {
@@ -669,30 +697,55 @@ extern "C" int petmh_advance(petmh_t* h, int n_sweeps) {
     }
     const int groups = (h->cfg.n_chains + chains_per_cta - 1) / chains_per_cta;
     const unsigned grid = (unsigned)((size_t)h->n_tac * groups);
-    const int half_at = h->plan_tune + (h->plan_draws + 1) / 2;   // first sweep of the second half
+    // Split halves as ArviZ's _split_chains: the first and the last n_half = draws / 2 draws of a chain (an odd
+    // middle draw belongs to neither).  Each half is cut into MOM_NBATCH batches of blen draws for the batch-means ESS
+    // of the moments mode; launches never straddle the tune / half / batch boundaries.
+    const int n_half = h->plan_draws / 2, half1_at = h->plan_draws - n_half;
+    const int blen = moments_batch_len(h->plan_draws);
     int left = n_sweeps;
     h->last_launches = 0;
     CU(cudaEventRecord(h->ev0, h->stream));
     while (left > 0) {
         int n = std::min(left, h->launch_sweeps);
-        // do not straddle the tune/draw boundary or the half boundary
-        if (h->sweep < h->plan_tune) n = std::min(n, h->plan_tune - h->sweep);
-        else if (h->sweep < half_at) n = std::min(n, half_at - h->sweep);
+        int half = -1, b_len = 0, b_idx = 0, b_end = 0;
+        if (h->sweep < h->plan_tune) {
+            n = std::min(n, h->plan_tune - h->sweep);
+        } else {
+            const int di = h->sweep - h->plan_tune;                       // draw index
+            int pos = -1;
+            if (di < n_half) { half = 0; pos = di; }
+            else if (di < half1_at) n = 1;                                // the dropped middle draw
+            else if (di < h->plan_draws) { half = 1; pos = di - half1_at; }
+            if (half >= 0) {
+                b_idx = blen > 0 ? pos / blen : 0;
+                if (blen > 0 && b_idx < MOM_NBATCH && (b_idx + 1) * blen <= n_half) {
+                    b_len = blen;
+                    n = std::min(n, (b_idx + 1) * blen - pos);
+                    b_end = pos + n == (b_idx + 1) * blen;
+                } else {
+                    n = std::min(n, n_half - pos);                        // leftover draws of the half: in no batch
+                }
+            }
+        }
         SweepParams p = base_params(h);
         p.sweep0 = h->sweep;
         p.n_sweeps = n;
         p.tune_until = h->plan_tune;
         p.thin = h->plan_thin;
-        const bool drawing = h->sweep >= h->plan_tune;
-        const int half = (drawing && h->sweep >= half_at) ? 1 : 0;
         p.mom_half = half;
-        p.mom_n_before = h->mom_n[half];
+        p.mom_n_before = half >= 0 ? h->mom_n[half] : 0;
+        p.batch_len = b_len;
+        p.batch_idx = b_idx;
+        p.batch_end = b_end;
         if (wide == 2) mh_sweep_kernel<0, false, 2><<<grid, nthr, smem_bytes_wide(), h->stream>>>(p);
         else if (wide) mh_sweep_kernel<0, false, 1><<<grid, nthr, smem_bytes_wide(), h->stream>>>(p);
         else if (h->variant == 0) mh_sweep_kernel<0, false><<<grid, nthr, smem_bytes(256), h->stream>>>(p);
         else mh_sweep_kernel<1, false><<<grid, nthr, smem_bytes(128), h->stream>>>(p);
         CU(cudaGetLastError());
-        if (drawing) { h->mom_n[half] += n; h->mom_launches[half] += 1; }
+        if (half >= 0) {
+            h->mom_n[half] += n;
+            if (b_end) h->mom_batches[half] = b_idx + 1;
+        }
         h->sweep += n;
         left -= n;
         h->last_launches++;
@@ -810,12 +863,84 @@ extern "C" int petmh_set_state(petmh_t* h, const float* q, const float* scale, i
     if (scale) CU(cudaMemcpyAsync(h->d_scale, scale, n * 4, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemsetAsync(h->d_cnt, 0, NCall * 96, h->stream));
     CU(cudaMemsetAsync(h->d_nacc, 0, NCall * 96 * sizeof(uint32_t), h->stream));
-    CU(cudaMemsetAsync(h->d_mom, 0, NCall * 96 * 6 * sizeof(float), h->stream));
+    CU(cudaMemsetAsync(h->d_mom, 0, NCall * 96 * 2 * MOMF * sizeof(float), h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->sweep = sweep;
     h->state_ready = true;
     h->mom_n[0] = h->mom_n[1] = 0;
-    h->mom_launches[0] = h->mom_launches[1] = 0;
+    h->mom_batches[0] = h->mom_batches[1] = 0;
+    return PETMH_OK;
+}
+
+// ---- full checkpoint: everything a run needs to continue exactly where it stopped ----------
+struct CkptHeader {
+    uint32_t magic, version;
+    int32_t n_tac, n_chains, max_draws, n_stored, plan_draws, plan_tune, plan_thin, sweep;
+    int32_t mom_n[2], mom_batches[2];
+    uint64_t seed;
+};
+static constexpr uint32_t CKPT_MAGIC = 0x50544d48u;   // "HMTP"
+
+extern "C" int64_t petmh_checkpoint_bytes(const petmh_t* h) {
+    if (!h || h->n_tac < 1) return 0;
+    const int64_t nc = (int64_t)h->n_tac * h->cfg.n_chains, ns = petmh_n_stored(h);
+    return (int64_t)sizeof(CkptHeader) + nc * 96 * (4 + 4 + 1 + 4 + 2 * MOMF * 4) + nc * ns * 96 * 4;
+}
+
+extern "C" int petmh_get_checkpoint(petmh_t* h, void* buf, int64_t nbytes) {
+    if (!h || !buf) return fail(h, PETMH_EINVAL, "null argument");
+    if (!h->state_ready || h->n_tac < 1) return fail(h, PETMH_EINVAL, "nothing to checkpoint: no data or chain state");
+    if (nbytes < petmh_checkpoint_bytes(h)) return fail(h, PETMH_EINVAL, "buffer too small: need %lld bytes", (long long)petmh_checkpoint_bytes(h));
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaStreamSynchronize(h->stream));
+    const size_t nc = (size_t)h->n_tac * h->cfg.n_chains, n = nc * 96;
+    const int ns = petmh_n_stored(h);
+    CkptHeader hd{CKPT_MAGIC, 2, h->n_tac, h->cfg.n_chains, h->cfg.max_draws, ns, h->plan_draws, h->plan_tune, h->plan_thin, h->sweep,
+                  {h->mom_n[0], h->mom_n[1]}, {h->mom_batches[0], h->mom_batches[1]}, h->cfg.seed};
+    unsigned char* o = static_cast<unsigned char*>(buf);
+    memcpy(o, &hd, sizeof hd); o += sizeof hd;
+    CU(cudaMemcpyAsync(o, h->d_q, n * 4, cudaMemcpyDeviceToHost, h->stream)); o += n * 4;
+    CU(cudaMemcpyAsync(o, h->d_scale, n * 4, cudaMemcpyDeviceToHost, h->stream)); o += n * 4;
+    CU(cudaMemcpyAsync(o, h->d_nacc, n * 4, cudaMemcpyDeviceToHost, h->stream)); o += n * 4;
+    CU(cudaMemcpyAsync(o, h->d_mom, n * 2 * MOMF * 4, cudaMemcpyDeviceToHost, h->stream)); o += n * 2 * MOMF * 4;
+    CU(cudaMemcpyAsync(o, h->d_cnt, n, cudaMemcpyDeviceToHost, h->stream)); o += n;
+    if (ns > 0)   // the stored slots of every chain: device [chain][max_draws][96] -> blob [chain][n_stored][96]
+        CU(cudaMemcpy2DAsync(o, (size_t)ns * 96 * 4, h->d_draws, (size_t)h->cfg.max_draws * 96 * 4, (size_t)ns * 96 * 4, nc,
+                             cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return PETMH_OK;
+}
+
+extern "C" int petmh_set_checkpoint(petmh_t* h, const void* buf, int64_t nbytes) {
+    if (!h || !buf) return fail(h, PETMH_EINVAL, "null argument");
+    if (nbytes < (int64_t)sizeof(CkptHeader)) return fail(h, PETMH_ESTATE, "checkpoint truncated");
+    CkptHeader hd;
+    memcpy(&hd, buf, sizeof hd);
+    if (hd.magic != CKPT_MAGIC || hd.version != 2) return fail(h, PETMH_ESTATE, "not a petmh checkpoint (or another version)");
+    if (hd.n_tac != h->n_tac || hd.n_chains != h->cfg.n_chains)
+        return fail(h, PETMH_ESTATE, "checkpoint holds %d TACs x %d chains, the handle has %d x %d bound (call petmh_set_data first)",
+                    hd.n_tac, hd.n_chains, h->n_tac, h->cfg.n_chains);
+    if (hd.n_stored > h->cfg.max_draws) return fail(h, PETMH_ESTATE, "checkpoint stores %d draws per chain, max_draws is %d", hd.n_stored, h->cfg.max_draws);
+    if (hd.seed != h->cfg.seed) return fail(h, PETMH_ESTATE, "checkpoint was taken with another seed: the continuation would not be the same run");
+    const size_t nc = (size_t)hd.n_tac * hd.n_chains, n = nc * 96;
+    const int64_t need = (int64_t)sizeof(CkptHeader) + (int64_t)n * (4 + 4 + 1 + 4 + 2 * MOMF * 4) + (int64_t)nc * hd.n_stored * 96 * 4;
+    if (nbytes < need) return fail(h, PETMH_ESTATE, "checkpoint truncated: %lld of %lld bytes", (long long)nbytes, (long long)need);
+    CU(cudaSetDevice(h->cfg.device));
+    const unsigned char* o = static_cast<const unsigned char*>(buf) + sizeof hd;
+    CU(cudaMemcpyAsync(h->d_q, o, n * 4, cudaMemcpyHostToDevice, h->stream)); o += n * 4;
+    CU(cudaMemcpyAsync(h->d_scale, o, n * 4, cudaMemcpyHostToDevice, h->stream)); o += n * 4;
+    CU(cudaMemcpyAsync(h->d_nacc, o, n * 4, cudaMemcpyHostToDevice, h->stream)); o += n * 4;
+    CU(cudaMemcpyAsync(h->d_mom, o, n * 2 * MOMF * 4, cudaMemcpyHostToDevice, h->stream)); o += n * 2 * MOMF * 4;
+    CU(cudaMemcpyAsync(h->d_cnt, o, n, cudaMemcpyHostToDevice, h->stream)); o += n;
+    if (hd.n_stored > 0)
+        CU(cudaMemcpy2DAsync(h->d_draws, (size_t)h->cfg.max_draws * 96 * 4, o, (size_t)hd.n_stored * 96 * 4, (size_t)hd.n_stored * 96 * 4, nc,
+                             cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->plan_draws = hd.plan_draws; h->plan_tune = hd.plan_tune; h->plan_thin = hd.plan_thin;
+    h->sweep = hd.sweep;
+    h->mom_n[0] = hd.mom_n[0]; h->mom_n[1] = hd.mom_n[1];
+    h->mom_batches[0] = hd.mom_batches[0]; h->mom_batches[1] = hd.mom_batches[1];
+    h->state_ready = true;
     return PETMH_OK;
 }
 
@@ -826,29 +951,31 @@ extern "C" int petmh_summary_device(petmh_t* h, float* d_out, void* stream) {
     CU(cudaSetDevice(h->cfg.device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     if (st != h->stream) CU(cudaStreamSynchronize(h->stream));
+    const int draw_sweeps = std::max(0, h->sweep - h->plan_tune);   // every non-tuning sweep counts accepted moves
+    if (h->d_draws && petmh_n_stored(h) >= 8) {
+        // stored draws: rank-normalised split R-hat, bulk/tail ESS, MCSE (ArviZ semantics)
+        if (!h->d_summary_ext) CU(cudaMalloc(&h->d_summary_ext, (size_t)h->cfg.max_tacs * 96 * 4 * sizeof(float)));
+        h->ext_sweep = -1;
+        rc = launch_rank_summary(h->d_draws, h->n_tac, h->cfg.n_chains, h->cfg.max_draws, petmh_n_stored(h), h->d_nacc, h->d_scale,
+                                 draw_sweeps, d_out, h->d_summary_ext, st);
+        if (rc) return fail(h, PETMH_ECUDA, "rank-diagnostics failed: %s", cudaGetErrorString((cudaError_t)rc));
+        h->ext_sweep = h->sweep;
+        return PETMH_OK;
+    }
     DiagParams dp{};
     dp.mom = h->d_mom;
     dp.mu = h->d_mu;
     dp.nacc = h->d_nacc;
     dp.scale = h->d_scale;
-    dp.draws = h->d_draws;
     dp.n_tacs = h->n_tac;
     dp.n_chains = h->cfg.n_chains;
-    dp.max_draws = h->cfg.max_draws;
-    dp.n_stored = petmh_n_stored(h);
     dp.n_half[0] = h->mom_n[0];
     dp.n_half[1] = h->mom_n[1];
-    dp.lag_terms[0] = h->mom_n[0] - h->mom_launches[0];
-    dp.lag_terms[1] = h->mom_n[1] - h->mom_launches[1];
+    dp.n_batch[0] = h->mom_batches[0];
+    dp.n_batch[1] = h->mom_batches[1];
+    dp.batch_len = moments_batch_len(h->plan_draws);
+    dp.n_draw_sweeps = draw_sweeps;
     dp.out = d_out;
-    if (h->d_draws && dp.n_stored >= 8) {
-        // stored draws: rank-normalised split R-hat, bulk/tail ESS, MCSE (ArviZ semantics)
-        const int draw_sweeps = std::max(0, std::min(h->sweep, h->plan_tune + h->plan_draws) - h->plan_tune);
-        rc = launch_rank_summary(h->d_draws, h->n_tac, h->cfg.n_chains, h->cfg.max_draws, dp.n_stored, h->d_nacc, h->d_scale,
-                                 draw_sweeps, d_out, st);
-        if (rc) return fail(h, PETMH_ECUDA, "rank-diagnostics failed: %s", cudaGetErrorString((cudaError_t)rc));
-        return PETMH_OK;
-    }
     rc = launch_summary(dp, st);
     if (rc) return fail(h, PETMH_ECUDA, "summary kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
     return PETMH_OK;
@@ -863,6 +990,77 @@ extern "C" int petmh_get_summary(petmh_t* h, float* out) {
     if (rc) return rc;
     CU(cudaMemcpyAsync(out, h->d_summary, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    return PETMH_OK;
+}
+
+extern "C" int petmh_get_summary_ext(petmh_t* h, float* out) {
+    if (!h || !out) return fail(h, PETMH_EINVAL, "null argument");
+    if (!h->d_draws || petmh_n_stored(h) < 8)
+        return fail(h, PETMH_EINVAL, "hdi / mcse_sd need stored draws (max_draws > 0 and >= 8 draws stored; have %d)", petmh_n_stored(h));
+    CU(cudaSetDevice(h->cfg.device));
+    if (h->ext_sweep != h->sweep || !h->d_summary_ext) {      // not computed for the current state yet
+        if (!h->d_summary) CU(cudaMalloc(&h->d_summary, (size_t)h->cfg.max_tacs * 96 * PETMH_N_STATS * sizeof(float)));
+        int rc = petmh_summary_device(h, h->d_summary, nullptr);
+        if (rc) return rc;
+    }
+    CU(cudaMemcpyAsync(out, h->d_summary_ext, (size_t)h->n_tac * 96 * 4 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return PETMH_OK;
+}
+
+// ---- handle-free summaries of gathered state (chains of one TAC sampled on several GPUs) -------------------------
+extern "C" int petmh_summary_from_draws_device(int device, const float* d_draws, int n_tac, int n_chains, int n_stored,
+                                               const uint32_t* d_nacc, const float* d_scale, int n_draw_sweeps,
+                                               float* d_out8, float* d_ext4, void* stream) {
+    if (!d_draws || !d_nacc || !d_scale || !d_out8 || n_tac < 1 || n_chains < 1 || n_stored < 8) {
+        g_create_error = "petmh_summary_from_draws_device: bad argument (needs >= 8 stored draws)";
+        return PETMH_EINVAL;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "cudaSetDevice failed"; return PETMH_ECUDA; }
+    const int rc = launch_rank_summary(d_draws, n_tac, n_chains, n_stored, n_stored, d_nacc, d_scale, n_draw_sweeps, d_out8, d_ext4,
+                                       (cudaStream_t)stream);
+    if (rc) { g_create_error = std::string("rank-diagnostics failed: ") + cudaGetErrorString((cudaError_t)rc); return PETMH_ECUDA; }
+    return PETMH_OK;
+}
+
+extern "C" int petmh_summary_from_moments_device(int device, const float* d_mom, const double* d_mu96, int n_tac, int n_chains,
+                                                 const int* n_half2, const int* n_batch2, int batch_len, const uint32_t* d_nacc,
+                                                 const float* d_scale, int n_draw_sweeps, float* d_out8, void* stream) {
+    if (!d_mom || !d_mu96 || !n_half2 || !n_batch2 || !d_nacc || !d_scale || !d_out8 || n_tac < 1 || n_chains < 1) {
+        g_create_error = "petmh_summary_from_moments_device: bad argument";
+        return PETMH_EINVAL;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "cudaSetDevice failed"; return PETMH_ECUDA; }
+    DiagParams dp{};
+    dp.mom = d_mom; dp.mu = d_mu96; dp.nacc = d_nacc; dp.scale = d_scale;
+    dp.n_tacs = n_tac; dp.n_chains = n_chains;
+    dp.n_half[0] = n_half2[0]; dp.n_half[1] = n_half2[1];
+    dp.n_batch[0] = n_batch2[0]; dp.n_batch[1] = n_batch2[1];
+    dp.batch_len = batch_len; dp.n_draw_sweeps = n_draw_sweeps; dp.out = d_out8;
+    const int rc = launch_summary(dp, (cudaStream_t)stream);
+    if (rc) { g_create_error = std::string("summary kernel failed: ") + cudaGetErrorString((cudaError_t)rc); return PETMH_ECUDA; }
+    return PETMH_OK;
+}
+
+// device pointers and counters of the handle's summary inputs, for gathering them across ranks (device memory owned by
+// the handle; valid until it is destroyed)
+extern "C" int petmh_export_summary_inputs(petmh_t* h, void** d_draws, void** d_mom, void** d_nacc, void** d_scale, void** d_mu96,
+                                           int* counters /*[8]: n_stored, max_draws, n_half0, n_half1, n_batch0, n_batch1, batch_len, n_draw_sweeps*/) {
+    if (!h) return PETMH_EINVAL;
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaStreamSynchronize(h->stream));
+    if (d_draws) *d_draws = h->d_draws;
+    if (d_mom) *d_mom = h->d_mom;
+    if (d_nacc) *d_nacc = h->d_nacc;
+    if (d_scale) *d_scale = h->d_scale;
+    if (d_mu96) *d_mu96 = h->d_mu;
+    if (counters) {
+        counters[0] = petmh_n_stored(h); counters[1] = h->cfg.max_draws;
+        counters[2] = h->mom_n[0]; counters[3] = h->mom_n[1];
+        counters[4] = h->mom_batches[0]; counters[5] = h->mom_batches[1];
+        counters[6] = moments_batch_len(h->plan_draws);
+        counters[7] = std::max(0, h->sweep - h->plan_tune);
+    }
     return PETMH_OK;
 }
 
@@ -951,6 +1149,8 @@ extern "C" int petmh_synth(petmh_t* h, int n_tac, uint64_t seed, const double* m
     if (!h->d_synth_truth) CU(cudaMalloc(&h->d_synth_truth, S * 96 * sizeof(float)));
     if (!h->d_synth_clean) CU(cudaMalloc(&h->d_synth_clean, S * 48 * NT * sizeof(float)));
     if (!h->d_synth_attempts) CU(cudaMalloc(&h->d_synth_attempts, S * sizeof(int)));
+    if (!h->d_synth_capped) CU(cudaMalloc(&h->d_synth_capped, sizeof(int)));
+    CU(cudaMemsetAsync(h->d_synth_capped, 0, sizeof(int), h->stream));
     CU(cudaMemcpyAsync(h->d_synth_f64, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     float* d_sig = reinterpret_cast<float*>(h->d_synth_f64 + buf.size());
     CU(cudaMemcpyAsync(d_sig, sig.data(), sig.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
@@ -959,6 +1159,8 @@ extern "C" int petmh_synth(petmh_t* h, int n_tac, uint64_t seed, const double* m
     sp.k2p = (float)k2p;
     sp.seed = seed;
     sp.tac_gid0 = h->cfg.tac_gid0;
+    sp.tac_gids = h->have_tac_gids ? h->d_tac_gids : nullptr;
+    sp.n_capped = h->d_synth_capped;
     sp.n_tac = n_tac;
     sp.y = h->d_y; sp.cref = h->d_cref; sp.k2p_out = h->d_k2p;
     sp.truth = h->d_synth_truth; sp.clean = h->d_synth_clean; sp.attempts = h->d_synth_attempts;
@@ -966,8 +1168,14 @@ extern "C" int petmh_synth(petmh_t* h, int n_tac, uint64_t seed, const double* m
     SweepParams p = base_params(h);
     synth_kernel<<<n_tac, 64, HOOK_SMEM, h->stream>>>(p, sp);
     CU(cudaGetLastError());
+    int capped = 0;
+    CU(cudaMemcpyAsync(&capped, h->d_synth_capped, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->have_data = true;
+    if (capped > 0)
+        return fail(h, PETMH_ESYNTH, "%d of %d synthetic TACs hit a rejection cap (4000 positivity redraws of one vector or 1000 "
+                    "negative-TAC redraws of the triple): their data is not a valid draw; petmh_synth_get's attempts[] is negative "
+                    "for them", capped, n_tac);
     return PETMH_OK;
 }
 

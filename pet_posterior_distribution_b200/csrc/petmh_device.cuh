@@ -31,6 +31,7 @@ constexpr int NCOL = PETMH_NCOL;     // 45 active columns of M
 constexpr int NGRID = 2 * NT;        // 108 resample points (kinetic_model.py:14)
 constexpr int MPACK = PETMH_MPACK;
 constexpr int SLOTS = 3;             // ROIs per lane
+constexpr int MOMF = 5;              // floats per (chain, half, coordinate) of running moments
 constexpr int TUNE_INTERVAL = 100;   // pymc Metropolis tune_interval
 constexpr float Z_CUT = 3.5f;        // erfc(z)/2 < 3.7e-7 beyond: below the fp32 rounding of a per-ROI sum (~1e2, ulp 8e-6)
 constexpr int RB = PETMH_RB;          // 18 rows per row block
@@ -75,6 +76,7 @@ struct FrameTables {
     int klo[NT], khi[NT];            // grid rows k with W_fwd[k, f] != 0 lie in [klo, khi]
     int acol[NCOL];                  // active column -> frame index
     int nrow[NT];                    // row j of M uses the first nrow[j] active columns
+    float tcol[NCOL + 3];            // frame end time (minutes, fp32) of each active column of M
     float inv_h;                     // 1/h of the Chebyshev range (fp32, as the kernel uses it)
     double cheb_c[NCOL][12];         // C[active column][d] for exactly that fp32 range (NCHMAX = 12)
     short pack_src[MPACK];           // packed M slot -> (row << 6 | active col) or -1
@@ -96,16 +98,23 @@ struct SweepParams {
     uint8_t* cnt;
     // outputs
     float* draws;           // [S*C][max_draws][96] or null
-    float* mom;             // [S*C][2 halves][96][3]: mean - mu, M2, lag-1 co-moment (Chan-merged per launch)
+    float* mom;             // [S*C][2 halves][96][MOMF]: mean - mu, M2, open batch sum, mean and M2 of the closed batch means
     int mom_n_before;       // draws already merged into this half
     uint32_t* nacc;         // [S*C][96] accepted moves in draw sweeps
-    float4* momw;           // [S*C][96] per-launch scratch: sum, sumsq, lag-1 products, previous draw (of q - ref)
-    float* mom_first;       // [S*C][96] first draw of the launch (q - ref)
+    float2* momw;           // [S*C][96] per-launch scratch: sum, sum of squares of q - ref (ref = q at launch start)
     int max_draws;          // capacity (stored draws per chain)
-    int mom_half;           // which half this launch accumulates into
+    int mom_half;           // which split half this launch's draws belong to; -1: not counted (ArviZ's split drops the
+                            // middle draw of an odd-length chain)
+    int batch_len;          // batch-means ESS: draws per batch (0: this launch's draws belong to no batch)
+    int batch_idx;          // index of the batch this launch's draws belong to (launches never straddle a batch)
+    int batch_end;          // this launch completes the batch
     int n_tacs, n_chains;
     int sweep0, n_sweeps, tune_until, thin;
     unsigned long long seed, tac_gid0;
+    // Philox stream of a chain: gid = tac_gid * chain_stride + chain_gid0 + local chain; tac_gid = tac_gids[tac] if given,
+    // else tac_gid0 + tac (defaults chain_stride = n_chains, chain_gid0 = 0: the chains of a TAC may be split over ranks)
+    const unsigned long long* tac_gids;
+    unsigned long long chain_gid0, chain_stride;
     // taped / debug mode (null in production)
     const float* tape_n;
     const float* tape_logu;
@@ -116,9 +125,6 @@ struct SweepParams {
     int tape_tac, tape_sweeps;
 };
 
-// frame end time (minutes) of each active column of M.  One frame grid per process:
-// petmh_set_frames refuses a second, different grid while it is loaded.
-__constant__ float c_tcol[NCOL + 3];   // (+3: the pipelined M.e loop computes exponentials up to 2 columns ahead)
 // triangle-aware column phases of the M.e loop (tools/gen_schedule.py)
 __constant__ int c_cend[PETMH_NBLK][PETMH_RB / 2] = PETMH_CEND;
 
@@ -243,7 +249,8 @@ __device__ __forceinline__ float half_erfc(float z) {
 constexpr int SM_CRS = 0;                                 // double [NGRID]
 constexpr int SM_M = SM_CRS + NGRID * 8;                  // float [MPACK]   packed operator
 constexpr int SM_A = SM_M + MPACK * 4;                    // float [APACK]   Chebyshev operator A = M C
-constexpr int SM_CR = SM_A + APACK * 4;                   // float [64]      reference TAC, [60] = k2p, [61] = inv_h
+constexpr int SM_TCOL = SM_A + APACK * 4;                 // float [48]      frame end time of each active column (exact path)
+constexpr int SM_CR = SM_TCOL + 48 * 4;                   // float [64]      reference TAC, [60] = k2p, [61] = inv_h
 constexpr int SM_YCC = SM_CR + 64 * 4;                    // float [48][YS]  -(y * cc)
 constexpr int SM_CC = SM_YCC + 48 * YS * 4;               // float [48][YS]  1/(sigma sqrt2)
 constexpr int SM_BAD = SM_CC + 48 * YS * 4;               // uchar [48] (+pad) 1 if any y < 0
@@ -430,6 +437,7 @@ __device__ __forceinline__ float exact_block(const int roi, const float dv, cons
     const float* crow0 = reinterpret_cast<const float*>(smem + SM_CC) + roi * YS;
     const u64 coefd = pack2(coef, coef), r1d = pack2(av, av);
     const float4* Mp = reinterpret_cast<const float4*>(sM + (blk == 0 ? 0 : (blk == 1 ? 220 : 780)));   // PETMH_MOFF
+    const float* tcol = reinterpret_cast<const float*>(smem + SM_TCOL);
     u64 acc[NPAIR];
 #pragma unroll
     for (int pq = 0; pq < NPAIR; pq++) acc[pq] = 0ull;
@@ -437,7 +445,7 @@ __device__ __forceinline__ float exact_block(const int roi, const float dv, cons
     // [cend[z-1], cend[z]) over pairs z..8 (tools/gen_schedule.py).
 #define PETMH_COL1(ZP)                                                                                           \
     {                                                                                                            \
-        const float e_ = ex2_approx(na * c_tcol[c]);                                                             \
+        const float e_ = ex2_approx(na * tcol[c]);                                                               \
         const u64 ed_ = pack2(e_, e_);                                                                           \
         if ((ZP) <= 1) { const float4 m = Mp[0]; if ((ZP) <= 0) ffma2(acc[0], pack2(m.x, m.y), ed_); ffma2(acc[1], pack2(m.z, m.w), ed_); } \
         if ((ZP) <= 3) { const float4 m = Mp[1]; if ((ZP) <= 2) ffma2(acc[2], pack2(m.x, m.y), ed_); ffma2(acc[3], pack2(m.z, m.w), ed_); } \
@@ -750,6 +758,7 @@ __device__ __forceinline__ void load_tac_image(const SweepParams& p, int tac, un
     build_crs(p.ft, cref, sCrs, tid, nthr);
     for (int i = tid; i < 64; i += nthr)
         sCr[i] = i < NT ? (float)cref[i] : (i == K2P_SLOT ? k2p : (i == INVH_SLOT ? inv_h : 0.f));
+    for (int i = tid; i < 48; i += nthr) reinterpret_cast<float*>(smem + SM_TCOL)[i] = p.ft->tcol[i];
     __syncthreads();
     build_operators(p.ft, sCrs, cref, sM, sA, reinterpret_cast<double*>(smem + SM_STATE), tid, nthr);
     const float* y = p.y + (size_t)tac * NROI * NT;
@@ -834,8 +843,8 @@ __global__ void __launch_bounds__(WIDE == 2 ? 288 : (WIDE == 1 ? 96 * WIDE_MAX_T
     const int chain = grp * chains_per_cta + warp * 2 + half;
     const bool active = chain < p.n_chains;
     const size_t cg = (size_t)tac * p.n_chains + (active ? chain : 0);   // local chain index (state arrays)
-    const unsigned long long gid = (p.tac_gid0 + (unsigned long long)tac) * (unsigned long long)p.n_chains +
-                                   (unsigned long long)(active ? chain : 0);
+    const unsigned long long gid = (p.tac_gids ? p.tac_gids[tac] : p.tac_gid0 + (unsigned long long)tac) * p.chain_stride +
+                                   p.chain_gid0 + (unsigned long long)(active ? chain : 0);
     float* xch = reinterpret_cast<float*>(smem + smem_bytes(256)) + triple * XCH_WORDS * 32 + lane;   // WIDE mailbox
 
     load_tac_image(p, tac, smem, tid, nthr);
@@ -899,7 +908,7 @@ __global__ void __launch_bounds__(WIDE == 2 ? 288 : (WIDE == 1 ? 96 * WIDE_MAX_T
                 ST_F(b * ST_BLOCK + 3 + s) = sc;
                 ST_I(b * ST_BLOCK + 6 + s) = cn;
                 ST_U(b * ST_BLOCK + 9 + s) = 0u;
-                if (!TAPED && active) p.momw[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (!TAPED && active) p.momw[o] = make_float2(0.f, 0.f);
             }
 #pragma unroll 1
         for (int b = 0; b < 2; b++) {
@@ -923,7 +932,6 @@ __global__ void __launch_bounds__(WIDE == 2 ? 288 : (WIDE == 1 ? 96 * WIDE_MAX_T
         const float3 v = eval_slots(q0[0][0], q0[0][1], q0[0][2], q0[1][0], q0[1][1], q0[1][2]);
         ll_old[0] = v.x; ll_old[1] = v.y; ll_old[2] = v.z;
     }
-    bool have_prev = false;
 
 #pragma unroll 1
     for (int it = 0; it < p.n_sweeps; it++) {
@@ -1046,31 +1054,42 @@ __global__ void __launch_bounds__(WIDE == 2 ? 288 : (WIDE == 1 ? 96 * WIDE_MAX_T
                     ST_F((c / SLOTS) * ST_BLOCK + (c % SLOTS));
         }
         if (!tuning) {
+            // one (uniform, unsigned) division per sweep
+            const unsigned di = (unsigned)(sweep - p.tune_until), dslot = di / (unsigned)p.thin;
+            const bool store = !TAPED && p.draws != nullptr && dslot * (unsigned)p.thin == di && dslot < (unsigned)p.max_draws;
+            if (store) __syncwarp();                                  // (warp-uniform) the chain's lanes read each other's state words below
             if (!TAPED && active) {
-                // one base address per array and one (uniform, unsigned) division per sweep; the six coordinates
-                // of the lane sit at compile-time offsets from the bases
-                const unsigned di = (unsigned)(sweep - p.tune_until), dslot = di / (unsigned)p.thin;
-                const bool store = p.draws != nullptr && dslot * (unsigned)p.thin == di && dslot < (unsigned)p.max_draws;
+                // one base address per array; the six coordinates of the lane sit at compile-time offsets from the bases
                 const size_t o0 = cg * 96 + l16;
-                const float* qref = p.q + o0;                         // ref = q at launch start (p.q is rewritten in the epilogue only)
-                float4* mw = p.momw + o0;
-                float* dst = p.draws + (cg * p.max_draws + dslot) * 96 + l16;   // (only dereferenced if store)
+                if (p.mom_half >= 0) {
+                    const float* qref = p.q + o0;                     // ref = q at launch start (p.q is rewritten in the epilogue only)
+                    float2* mw = p.momw + o0;
 #pragma unroll
-                for (int c = 0; c < 2 * SLOTS; c++) {
-                    const int off = (c / SLOTS) * 48 + (c % SLOTS) * 16;
-                    const float qv = ST_F((c / SLOTS) * ST_BLOCK + (c % SLOTS));
-                    const float x = qv - qref[off];
-                    float4 m = mw[off];
-                    m.x += x;
-                    m.y = fmaf(x, x, m.y);
-                    if (have_prev) m.z = fmaf(x, m.w, m.z);
-                    else p.mom_first[o0 + off] = x;                   // first draw of this launch
-                    m.w = x;
-                    mw[off] = m;
-                    if (store) dst[off] = qv;
+                    for (int c = 0; c < 2 * SLOTS; c++) {
+                        const int off = (c / SLOTS) * 48 + (c % SLOTS) * 16;
+                        const float x = ST_F((c / SLOTS) * ST_BLOCK + (c % SLOTS)) - qref[off];
+                        float2 m = mw[off];
+                        m.x += x;
+                        m.y = fmaf(x, x, m.y);
+                        mw[off] = m;
+                    }
+                }
+                if (store) {
+                    // thinned draw [2][48] f32 = 24 float4 per chain, written as 128-bit stores: lane l16 moves float4
+                    // number l16 and, for l16 < 8, number 16 + l16, read from the chain's state rows in shared memory
+                    // (row (b, s) = 16 consecutive floats)
+                    float4* dst = reinterpret_cast<float4*>(p.draws + (cg * p.max_draws + dslot) * 96);
+                    const float* stc = st - l16;
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int k = h * 16 + l16;                   // float4 index, coordinates 4k .. 4k+3
+                        if (k < 24) {
+                            const int b = k / 12, r = k - 12 * b;     // r / 4 = ROI slot, 4 (r % 4) = first lane
+                            dst[k] = *reinterpret_cast<const float4*>(stc + (b * ST_BLOCK + (r >> 2)) * ST_STRIDE + 4 * (r & 3));
+                        }
+                    }
                 }
             }
-            have_prev = true;
         }
     }
     // ---- epilogue: persist state and moments ----
@@ -1089,22 +1108,29 @@ __global__ void __launch_bounds__(WIDE == 2 ? 288 : (WIDE == 1 ? 96 * WIDE_MAX_T
             p.scale[o] = ST_F(b * ST_BLOCK + 3 + s);
             p.cnt[o] = (uint8_t)ST_I(b * ST_BLOCK + 6 + s);
             p.nacc[o] += ST_U(b * ST_BLOCK + 9 + s);
-            if (nb > 0) {
-                float* mo = p.mom + ((cg * 2 + p.mom_half) * 96 + b * 48 + i) * 3;
-                const float4 mw = p.momw[o];
-                const double sum = mw.x, sq = mw.y, lag = mw.z;
+            if (nb > 0 && p.mom_half >= 0) {
+                float* mo = p.mom + ((cg * 2 + p.mom_half) * 96 + b * 48 + i) * MOMF;
+                const float2 mw = p.momw[o];
+                const double sum = mw.x, sq = mw.y;
                 const double ref = (double)qref - p.mu[b * 48 + i];                    // launch reference about mu
-                const double x0 = p.mom_first[o], xl = mw.w;
                 const double mean_r = sum / nb;                                        // about ref
                 const double M2_b = sq - sum * mean_r;
-                // sum_t (x_t - m)(x_{t-1} - m), t = 1..nb-1, exactly
-                const double C1_b = lag - mean_r * (2.0 * sum - x0 - xl) + (nb - 1) * mean_r * mean_r;
                 const double mean_b = ref + mean_r;                                    // about mu
                 const double na = p.mom_n_before, n = na + nb;
                 const double mean_a = mo[0], delta = mean_b - mean_a;
                 mo[0] = (float)(mean_a + delta * nb / n);
                 mo[1] = (float)((double)mo[1] + M2_b + delta * delta * na * nb / n);
-                mo[2] = (float)((double)mo[2] + C1_b);
+                if (p.batch_len > 0) {                                                 // batch means (ESS in moments mode)
+                    double cur = (double)mo[2] + mean_b * nb;                          // sum of q - mu over the open batch
+                    if (p.batch_end) {
+                        const double bm = cur / p.batch_len, k = p.batch_idx + 1;
+                        const double m_old = mo[3], dlt = bm - m_old, m_new = m_old + dlt / k;
+                        mo[3] = (float)m_new;
+                        mo[4] = (float)((double)mo[4] + dlt * (bm - m_new));
+                        cur = 0.0;
+                    }
+                    mo[2] = (float)cur;
+                }
             }
         }
     }
@@ -1165,7 +1191,7 @@ __global__ void forward_srtm_kernel(const SweepParams p, int tac, const float* d
         const float k2a = k2[r] / dvr[r];
         const float na = k2a * -1.4426950408889634f;
         float conv = 0.f;
-        for (int c = 0; c < NCOL; c++) conv = fmaf(Md[j * NCOL + c], ex2_approx(na * c_tcol[c]), conv);
+        for (int c = 0; c < NCOL; c++) conv = fmaf(Md[j * NCOL + c], ex2_approx(na * p.ft->tcol[c]), conv);
         tac_out[idx] = fmaf(fmaf(-r1[r], k2a, k2[r]), conv, r1[r] * cr[j]);
     }
 }
@@ -1216,7 +1242,7 @@ __global__ void init_state_kernel(float* q, float* scale, uint8_t* cnt, uint32_t
         cnt[i] = 0;
         nacc[i] = 0;
     }
-    if (i < n_chains_total * 96 * 6) mom[i] = 0.f;
+    if (i < n_chains_total * 96 * 2 * MOMF) mom[i] = 0.f;
 }
 
 __global__ void convert_data_kernel(const double* y64, const double* cref64, const double* k2p64, float* y, double* cref,

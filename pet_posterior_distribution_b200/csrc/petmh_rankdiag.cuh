@@ -99,10 +99,12 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
     return t;
 }
 
-// series value of type ty at element e: 0 = z (bulk), 1 = x <= q05, 2 = x <= q95, 3 = x
+// series value of type ty at element e: 0 = z (bulk), 1 = x <= q05, 2 = x <= q95, 3 = x, 4 = x^2 (arviz _ess_sd)
+constexpr int N_SERIES = 5;
 __device__ __forceinline__ float series(int ty, const float* xs, const float* z, float q05, float q95, size_t e) {
     if (ty == 0) return z[e];
     if (ty == 3) return xs[e];
+    if (ty == 4) return xs[e] * xs[e];
     const float x = xs[e];
     return (ty == 1 ? x <= q05 : x <= q95) ? 1.f : 0.f;
 }
@@ -132,18 +134,21 @@ __global__ void rd_rhat(const float* z, const float* zf, int m, int h, float* rh
     if (threadIdx.x == 0) rhat_out[seg] = best;
 }
 
-// arviz _ess for one (segment, series type); blockDim.x = ESS_LB lags per batch
-constexpr int ESS_LB = 256, ESS_LAGS = 64;
-constexpr int ESS_STAGE_MAX_H = 6144;   // 4 chain groups x h floats of dynamic shared memory (<= 96 KB)
+// arviz _ess for one (segment, series type).  A batch of lags = ESS_LB / ng lags x ng chain groups; ng (4, 2 or 1) is
+// the number of chains staged in dynamic shared memory at a time (ng x h floats, up to ESS_STAGE_BYTES): h = 10 000 (the
+// reference's 20 000 draws) stages 4 chains, h <= 51 200 one; beyond that (staged = 0) the fp64 path reads global memory.
+constexpr int ESS_LB = 256;
+constexpr int ESS_STAGE_BYTES = 200 * 1024;
 __global__ void __launch_bounds__(ESS_LB) rd_ess(const float* xs, const float* z, const float* q05, const float* q95, int m,
-                                                 int h, float* rho_scratch /*[nseg*4][h]*/, float* ess_out /*[nseg][4]*/,
-                                                 int staged /* dynamic smem holds 4 x h floats */) {
+                                                 int h, float* rho_scratch /*[nseg*N_SERIES][h]*/, float* ess_out /*[nseg][N_SERIES]*/,
+                                                 int staged /* dynamic smem holds ng x h floats */, int ng) {
     extern __shared__ float ess_stage[];   // [chain group][h]: the centred series of the chain the group is working on
     __shared__ double sh[32];
     __shared__ double cmean[2048];
     __shared__ int s_stop, s_t;
     __shared__ double s_even, s_odd;
-    const int seg = blockIdx.x >> 2, ty = blockIdx.x & 3, tid = threadIdx.x;
+    const int seg = blockIdx.x / N_SERIES, ty = blockIdx.x % N_SERIES, tid = threadIdx.x;
+    const int ESS_LAGS = ESS_LB / ng;
     const size_t base = (size_t)seg * m * h;
     const float a05 = q05[seg], a95 = q95[seg];
     float* rho = rho_scratch + (size_t)blockIdx.x * h;
@@ -165,7 +170,7 @@ __global__ void __launch_bounds__(ESS_LB) rd_ess(const float* xs, const float* z
     if (m > 1) var_plus += (sum_mean2 - sum_mean * sum_mean / m) / (m - 1);
     const double ntot = (double)m * h;
     if (!(var_plus > 0.0) || h < 4) {
-        if (tid == 0) ess_out[seg * 4 + ty] = CUDART_NAN_F;
+        if (tid == 0) ess_out[seg * N_SERIES + ty] = CUDART_NAN_F;
         return;
     }
     if (tid == 0) { s_stop = 0; s_t = 1; s_even = 1.0; s_odd = 0.0; rho[0] = 1.f; }
@@ -184,7 +189,7 @@ __global__ void __launch_bounds__(ESS_LB) rd_ess(const float* xs, const float* z
             // rounding x - mean to fp32 is below their own quantisation) and forms the lag products with fp32 FMAs in
             // chunks of 8, added up in fp64 -- one LDS + one FFMA per product instead of two conversions, two fp64
             // subtractions and a DFMA (the loop was bound by the FP64 pipe).  Uniform trip count: barriers inside.
-            constexpr int NG = ESS_LB / ESS_LAGS;
+            const int NG = ng;
             float* cb = ess_stage + (size_t)grp * h;
             for (int c0 = 0; c0 < m; c0 += NG) {
                 const int c = c0 + grp;
@@ -215,7 +220,7 @@ __global__ void __launch_bounds__(ESS_LB) rd_ess(const float* xs, const float* z
                 }
             }
         } else if (t < h) {
-            for (int c = grp; c < m; c += ESS_LB / ESS_LAGS) {
+            for (int c = grp; c < m; c += ng) {
                 const double mu = cmean[min(c, 2047)];
                 const size_t o = base + (size_t)c * h;
                 // four independent partial sums: the loop is bound by the latency of the fp64 accumulation chain
@@ -235,7 +240,7 @@ __global__ void __launch_bounds__(ESS_LB) rd_ess(const float* xs, const float* z
         part[tid] = acc;
         __syncthreads();
         if (grp == 0 && t < h) {
-            for (int g2 = 1; g2 < ESS_LB / ESS_LAGS; g2++) acc += part[g2 * ESS_LAGS + tl];
+            for (int g2 = 1; g2 < ng; g2++) acc += part[g2 * ESS_LAGS + tl];
             rho[t] = (float)(1.0 - (mean_var - acc / m) / var_plus);
         }
         __syncthreads();
@@ -278,45 +283,90 @@ __global__ void __launch_bounds__(ESS_LB) rd_ess(const float* xs, const float* z
         for (int i = 0; i <= max_t; i++) ssum += rho[i];
         double tau = -1.0 + 2.0 * ssum + ((max_t + 1 >= 0 && max_t + 1 < h) ? (double)rho[max_t + 1] : 0.0);
         tau = fmax(tau, 1.0 / log10(ntot));
-        ess_out[seg * 4 + ty] = (float)(ntot / tau);
+        ess_out[seg * N_SERIES + ty] = (float)(ntot / tau);
     }
 }
 
-// pooled mean / sd (ddof = 1) of a segment's values + assembly of the 8-column row
-__global__ void rd_finalize(const float* xs, int L, const float* ess, const float* rhat, const uint32_t* nacc,
-                            const float* scale, int n_chains, int tac0, int n_draw_sweeps, float* out) {
+// arviz hdi (unimodal, hdi_prob): the narrowest interval holding floor(prob L) + 1 of the segment's sorted values;
+// one CTA per segment, first minimum wins (numpy argmin)
+__global__ void rd_hdi(const unsigned long long* keys, int L, double prob, float* lo_out, float* hi_out) {
+    __shared__ float s_w[32];
+    __shared__ int s_i[32];
+    const int seg = blockIdx.x, tid = threadIdx.x;
+    const unsigned long long* k = keys + (size_t)seg * L;
+    const int inc = (int)floor(prob * L), n_int = L - inc;
+    float best = CUDART_INF_F;
+    int bi = 0x7fffffff;
+    if (inc >= 1 && n_int >= 1) {
+        for (int i = tid; i < n_int; i += blockDim.x) {
+            const float w = (float)((double)sortable2f((uint32_t)k[i + inc]) - (double)sortable2f((uint32_t)k[i]));
+            if (w < best) { best = w; bi = i; }      // (ascending i per thread: keeps the first minimum)
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const float w2 = __shfl_down_sync(0xffffffffu, best, o);
+        const int i2 = __shfl_down_sync(0xffffffffu, bi, o);
+        if (w2 < best || (w2 == best && i2 < bi)) { best = w2; bi = i2; }
+    }
+    if ((tid & 31) == 0) { s_w[tid >> 5] = best; s_i[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++)
+            if (s_w[w] < best || (s_w[w] == best && s_i[w] < bi)) { best = s_w[w]; bi = s_i[w]; }
+        if (bi == 0x7fffffff) { lo_out[seg] = sortable2f((uint32_t)k[0]); hi_out[seg] = sortable2f((uint32_t)k[L - 1]); }
+        else { lo_out[seg] = sortable2f((uint32_t)k[bi]); hi_out[seg] = sortable2f((uint32_t)k[bi + inc]); }
+    }
+}
+
+// pooled mean / sd (ddof = 1) over ALL stored draws of a segment (pm.summary does not split; for an odd number of
+// draws the split series drop the middle one) + assembly of the 8-column row and of the 4 extra pm.summary columns
+__global__ void rd_finalize(const RankDiagParams p, const float* ess, const float* rhat, const float* hlo, const float* hhi,
+                            const uint32_t* nacc, const float* scale, int n_draw_sweeps, float* out, float* ext) {
     __shared__ double sh[32];
     const int seg = blockIdx.x;
-    const float* a = xs + (size_t)seg * L;
+    const int tac = p.tac0 + seg / 96, coord = seg % 96;
+    const int n = p.n_chains * p.n_stored;
+    auto val = [&](int i) {
+        const int c = i / p.n_stored, d = i - c * p.n_stored;
+        return (double)p.draws[(((size_t)tac * p.n_chains + c) * p.max_draws + d) * 96 + coord];
+    };
     double s = 0;
-    for (int i = threadIdx.x; i < L; i += blockDim.x) s += a[i];
-    const double mean = block_sum(s, sh) / L;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += val(i);
+    const double mean = block_sum(s, sh) / n;
     double q = 0;
-    for (int i = threadIdx.x; i < L; i += blockDim.x) { const double d = a[i] - mean; q += d * d; }
-    const double sd = sqrt(block_sum(q, sh) / (L - 1));
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { const double d = val(i) - mean; q += d * d; }
+    const double sd = sqrt(block_sum(q, sh) / (n - 1));
     if (threadIdx.x == 0) {
-        const int tac = tac0 + seg / 96, coord = seg % 96;
         double acc = 0, sc = 0;
-        for (int c = 0; c < n_chains; c++) {
-            acc += nacc[((size_t)tac * n_chains + c) * 96 + coord];
-            sc += scale[((size_t)tac * n_chains + c) * 96 + coord];
+        for (int c = 0; c < p.n_chains; c++) {
+            acc += nacc[((size_t)tac * p.n_chains + c) * 96 + coord];
+            sc += scale[((size_t)tac * p.n_chains + c) * 96 + coord];
         }
+        const float* e = ess + (size_t)seg * N_SERIES;
         float* o = out + ((size_t)tac * 96 + coord) * 8;
         o[0] = (float)mean;
         o[1] = (float)sd;
-        o[2] = (float)(sd / sqrt((double)ess[seg * 4 + 3]));
-        o[3] = ess[seg * 4 + 0];
-        o[4] = fminf(ess[seg * 4 + 1], ess[seg * 4 + 2]);
+        o[2] = (float)(sd / sqrt((double)e[3]));
+        o[3] = e[0];
+        o[4] = fminf(e[1], e[2]);
         o[5] = rhat[seg];
-        o[6] = n_draw_sweeps > 0 ? (float)(acc / ((double)n_chains * n_draw_sweeps)) : CUDART_NAN_F;
-        o[7] = (float)(sc / n_chains);
+        o[6] = n_draw_sweeps > 0 ? (float)(acc / ((double)p.n_chains * n_draw_sweeps)) : CUDART_NAN_F;
+        o[7] = (float)(sc / p.n_chains);
+        if (ext) {   // hdi_3%, hdi_97%, mcse_sd, ess_sd (arviz _mcse_sd / _ess_sd)
+            float* x = ext + ((size_t)tac * 96 + coord) * 4;
+            const double esd = fmin((double)e[3], (double)e[4]);
+            x[0] = hlo[seg];
+            x[1] = hhi[seg];
+            x[2] = (float)(sd * sqrt(exp(1.0) * pow(1.0 - 1.0 / esd, esd - 1.0) - 1.0));
+            x[3] = (float)esd;
+        }
     }
 }
 
 // Host driver.  Returns a cudaError_t (0 = ok).
 static inline int launch_rank_summary(const float* d_draws, int n_tac_total, int n_chains, int max_draws, int n_stored,
                                       const uint32_t* nacc, const float* scale, int n_draw_sweeps, float* d_out,
-                                      cudaStream_t st) {
+                                      float* d_ext /*[n_tac][96][4] or null*/, cudaStream_t st) {
     const int h = n_stored / 2;
     const int m = 2 * n_chains;
     const int L = m * h;
@@ -326,7 +376,7 @@ static inline int launch_rank_summary(const float* d_draws, int n_tac_total, int
     tacs_per_batch = std::min(tacs_per_batch, n_tac_total);
     const size_t nseg_b = (size_t)tacs_per_batch * 96, nmax = nseg_b * L;
     float *xs = nullptr, *z = nullptr, *zf = nullptr, *med = nullptr, *q05 = nullptr, *q95 = nullptr, *rho = nullptr, *ess = nullptr,
-          *rhat = nullptr;
+          *rhat = nullptr, *hlo = nullptr, *hhi = nullptr;
     unsigned long long *k0 = nullptr, *k1 = nullptr;
     uint32_t *v0 = nullptr, *v1 = nullptr;
     void* tmp = nullptr;
@@ -337,7 +387,8 @@ static inline int launch_rank_summary(const float* d_draws, int n_tac_total, int
     RD(cudaMallocAsync(&xs, nmax * 4, st)); RD(cudaMallocAsync(&z, nmax * 4, st)); RD(cudaMallocAsync(&zf, nmax * 4, st));
     RD(cudaMallocAsync(&k0, nmax * 8, st)); RD(cudaMallocAsync(&k1, nmax * 8, st)); RD(cudaMallocAsync(&v0, nmax * 4, st)); RD(cudaMallocAsync(&v1, nmax * 4, st));
     RD(cudaMallocAsync(&med, nseg_b * 4, st)); RD(cudaMallocAsync(&q05, nseg_b * 4, st)); RD(cudaMallocAsync(&q95, nseg_b * 4, st));
-    RD(cudaMallocAsync(&rho, nseg_b * 4 * (size_t)h * 4, st)); RD(cudaMallocAsync(&ess, nseg_b * 4 * 4, st)); RD(cudaMallocAsync(&rhat, nseg_b * 4, st));
+    RD(cudaMallocAsync(&rho, nseg_b * N_SERIES * (size_t)h * 4, st)); RD(cudaMallocAsync(&ess, nseg_b * N_SERIES * 4, st)); RD(cudaMallocAsync(&rhat, nseg_b * 4, st));
+    RD(cudaMallocAsync(&hlo, nseg_b * 4, st)); RD(cudaMallocAsync(&hhi, nseg_b * 4, st));
     {
         int seg_bits = 1;
         while (((size_t)1 << seg_bits) < nseg_b) seg_bits++;
@@ -352,17 +403,20 @@ static inline int launch_rank_summary(const float* d_draws, int n_tac_total, int
             RD(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k0, k1, v0, v1, n, 0, 32 + seg_bits, st));
             rd_ranks<<<gb, 256, 0, st>>>(k1, v1, z, L, n);
             rd_quantiles<<<(nseg + 127) / 128, 128, 0, st>>>(k1, L, nseg, med, q05, q95);
+            rd_hdi<<<nseg, 256, 0, st>>>(k1, L, 0.94, hlo, hhi);
             rd_build_keys<<<gb, 256, 0, st>>>(p, 1, med, xs, k0, v0, n);
             RD(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k0, k1, v0, v1, n, 0, 32 + seg_bits, st));
             rd_ranks<<<gb, 256, 0, st>>>(k1, v1, zf, L, n);
             rd_rhat<<<nseg, 256, 0, st>>>(z, zf, m, h, rhat);
             {
-                const int staged = h <= ESS_STAGE_MAX_H ? 1 : 0;
-                const size_t dyn = staged ? (size_t)(ESS_LB / ESS_LAGS) * h * sizeof(float) : 0;
+                const size_t per_chain = (size_t)h * sizeof(float);
+                const int ng = 4 * per_chain <= (size_t)ESS_STAGE_BYTES ? 4 : (2 * per_chain <= (size_t)ESS_STAGE_BYTES ? 2 : 1);
+                const int staged = (size_t)ng * per_chain <= (size_t)ESS_STAGE_BYTES ? 1 : 0;
+                const size_t dyn = staged ? (size_t)ng * per_chain : 0;
                 if (dyn > 16 * 1024) RD(cudaFuncSetAttribute(rd_ess, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-                rd_ess<<<nseg * 4, ESS_LB, dyn, st>>>(xs, z, q05, q95, m, h, rho, ess, staged);
+                rd_ess<<<nseg * N_SERIES, ESS_LB, dyn, st>>>(xs, z, q05, q95, m, h, rho, ess, staged, staged ? ng : 4);
             }
-            rd_finalize<<<nseg, 256, 0, st>>>(xs, L, ess, rhat, nacc, scale, n_chains, t0, n_draw_sweeps, d_out);
+            rd_finalize<<<nseg, 256, 0, st>>>(p, ess, rhat, hlo, hhi, nacc, scale, n_draw_sweeps, d_out, d_ext);
             RD(cudaGetLastError());
         }
         RD(cudaStreamSynchronize(st));
@@ -370,7 +424,7 @@ static inline int launch_rank_summary(const float* d_draws, int n_tac_total, int
 done:
 #undef RD
     {
-        void* bufs[] = {xs, z, zf, k0, k1, v0, v1, med, q05, q95, rho, ess, rhat, tmp};
+        void* bufs[] = {xs, z, zf, k0, k1, v0, v1, med, q05, q95, rho, ess, rhat, hlo, hhi, tmp};
         for (void* b : bufs) if (b) cudaFreeAsync(b, st);
         cudaStreamSynchronize(st);
     }

@@ -18,7 +18,9 @@ struct SynthParams {
     const float* sigma;      // [48][54] sigma_noise
     float k2p;
     unsigned long long seed, tac_gid0;
+    const unsigned long long* tac_gids;   // optional explicit global TAC ids
     int n_tac;
+    int* n_capped;           // number of TACs that hit a rejection cap (their data is NOT a valid draw)
     // outputs
     float* y;                // [S][48][54]
     double* cref;            // [S][54]
@@ -43,7 +45,8 @@ __global__ void __launch_bounds__(64) synth_kernel(const SweepParams p, const Sy
     __shared__ double z[64];
     __shared__ double xv[3][64];
     const int tid = threadIdx.x, tac = blockIdx.x;
-    const unsigned long long gid = sp.tac_gid0 + tac;
+    const unsigned long long gid = sp.tac_gids ? sp.tac_gids[tac] : sp.tac_gid0 + tac;
+    bool capped = false;
     float* scratch = reinterpret_cast<float*>(smem + SM_STATE);   // [32 lanes][3][54] clean TAC by lane
     int attempt = 0;
     while (true) {
@@ -62,9 +65,11 @@ __global__ void __launch_bounds__(64) synth_kernel(const SweepParams p, const Sy
                 }
                 const int neg = __syncthreads_or(tid < sp.dim[v] && acc < 0.0);
                 tries++;
-                if (!neg || tries > 4000) break;
+                if (!neg) break;
+                if (tries > 4000) { capped = true; break; }
             }
         }
+        if (capped) break;   // (CTA-uniform) a vector could not be drawn positive: give up on this TAC
         // ---- forward simulation through the production routine ----
         if (tid < NT) sp.cref[(size_t)tac * NT + tid] = xv[2][tid];
         if (tid == 0) sp.k2p_out[tac] = sp.k2p;
@@ -85,7 +90,8 @@ __global__ void __launch_bounds__(64) synth_kernel(const SweepParams p, const Sy
         }
         neg = __syncthreads_or(neg);
         attempt++;
-        if (!neg || attempt > 1000) break;
+        if (!neg) break;
+        if (attempt > 1000) { capped = true; break; }
     }
     // ---- noise: x + sqrt(x) * TruncNormal(0, sigma, low = -sqrt(x))  (sample_sim_data.py:205-215) ----
     for (int i = tid; i < 48 * NT; i += 64) {
@@ -108,7 +114,11 @@ __global__ void __launch_bounds__(64) synth_kernel(const SweepParams p, const Sy
         sp.truth[(size_t)tac * 96 + tid] = (float)xv[0][tid];
         sp.truth[(size_t)tac * 96 + 48 + tid] = (float)xv[1][tid];
     }
-    if (tid == 0) sp.attempts[tac] = attempt;
+    // (capped is CTA-uniform: it derives from __syncthreads_or results)
+    if (tid == 0) {
+        sp.attempts[tac] = capped ? -(attempt + 1) : attempt;   // negative: a rejection cap was hit
+        if (capped) atomicAdd(sp.n_capped, 1);
+    }
 }
 
 }  // namespace petmh

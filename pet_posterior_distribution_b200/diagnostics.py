@@ -1,9 +1,9 @@
 """Host-side writers for the reference's side outputs (mcmc.py:162-194): the per-sample
 pickle, the ArviZ-style ``_summary.csv`` and the ``rhat_less_than_102.txt`` log.
 
-mean / sd / mcse_mean / ess_bulk / ess_tail / r_hat come from the GPU (K3, petmh_get_summary);
-the two remaining pm.summary columns that need order statistics of the pooled draws
-(hdi_3%, hdi_97%) and mcse_sd are computed here from the chains with numpy.
+Every pm.summary column comes from the GPU: mean / sd / mcse_mean / ess_bulk / ess_tail / r_hat from
+petmh_get_summary, hdi_3% / hdi_97% / mcse_sd from petmh_get_summary_ext (K3, stored draws).  The numpy ``hdi`` /
+``mcse_sd`` below remain only for callers that pass no GPU columns (fewer than 8 stored draws).
 """
 import io
 import os
@@ -31,18 +31,21 @@ def mcse_sd(x, ess_sd):
     return sd * fac
 
 
-def summary_csv(dvr, r1, k2p, gpu_summary, ess_sd=None):
+def summary_csv(dvr, r1, k2p, gpu_summary, gpu_ext=None):
     """CSV text with pm.summary's layout: rows var_DVR[i], var_R1[i], var_k2p; columns
     mean, sd, hdi_3%, hdi_97%, mcse_mean, mcse_sd, ess_bulk, ess_tail, r_hat (default rounding:
-    3 decimals, ESS to 0 decimals, r_hat to 2).  dvr/r1: (chains, draws, 48); gpu_summary (96, 8)."""
+    3 decimals, ESS to 0 decimals, r_hat to 2).  dvr/r1: (chains, draws, 48); gpu_summary (96, 8) from
+    MHSampler.summary(), gpu_ext (96, 4) = hdi_3%, hdi_97%, mcse_sd, ess_sd from MHSampler.summary_ext()."""
     out = io.StringIO()
     out.write(",mean,sd,hdi_3%,hdi_97%,mcse_mean,mcse_sd,ess_bulk,ess_tail,r_hat\n")
     for b, (name, arr) in enumerate((("var_DVR", dvr), ("var_R1", r1))):
         for i in range(arr.shape[-1]):
             g = gpu_summary[b * 48 + i]
-            lo, hi = hdi(arr[..., i])
-            # ess_sd ~ ess_bulk is the standard fallback when the squared-deviation ESS is not computed
-            msd = mcse_sd(arr[..., i], g[3] if ess_sd is None else ess_sd[b * 48 + i])
+            if gpu_ext is not None:
+                lo, hi, msd = gpu_ext[b * 48 + i][:3]
+            else:        # too few stored draws for the GPU path: numpy, with ess_sd ~ ess_bulk
+                lo, hi = hdi(arr[..., i])
+                msd = mcse_sd(arr[..., i], g[3])
             out.write("%s[%d],%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.1f,%.1f,%.2f\n" %
                       (name, i, g[0], g[1], lo, hi, g[2], msd, np.round(g[3]), np.round(g[4]), g[5]))
     k = float(np.asarray(k2p).reshape(-1)[0])

@@ -11,6 +11,9 @@ Differences by design: ``chains`` is honoured (the reference never passes it to 
 all pending test samples run as ONE batch on the GPU instead of a Python loop, and the
 module does nothing at import time -- run ``python -m pet_posterior_distribution_b200.mcmc``
 (from the directory that holds ``sim_data/`` and ``prior_stats_nROI48.pik``) or call main().
+Under ``torchrun --nproc-per-node N -m pet_posterior_distribution_b200.mcmc`` the pending samples are sharded over
+N GPUs (by sample when there are at least N of them, else by chain: distributed.run_sharded) and every rank
+writes the files of the samples it owns.
 """
 import glob
 import os
@@ -74,6 +77,41 @@ def save_name(km_obs):
         n_ROI_test, iter_mcmc, burn_mcmc, km_obs['DVR'][0], km_obs['R1'][0], km_obs['k2p'][0])
 
 
+def _dist_context():
+    """(rank, world, local_rank, initialised_here).  Under torchrun (WORLD_SIZE > 1) the pending samples are sharded over
+    the ranks, one process per GPU (NCCL); otherwise a single process on one GPU."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world <= 1:
+        return 0, 1, None, False
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    here = False
+    if not dist.is_initialized():
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        here = True
+    return dist.get_rank(), dist.get_world_size(), local, here
+
+
+def _write_sample(mcmc_roi_dir, fname, sample_plot, km_obs, dvr, r1, y_obs, summ, ext, elapsed):
+    """The three per-sample outputs of mcmc.py:162-194."""
+    DVR_mcmc = dvr.astype(NP_DTYPE)
+    R1_mcmc = r1.astype(NP_DTYPE)
+    k2p_mcmc = np.full(DVR_mcmc.shape[:2], km_obs['k2p'][0])
+    save_mcmc_dic = {
+        'idata': diagnostics.make_idata(DVR_mcmc, R1_mcmc, km_obs['k2p'], {'scaling': summ[:, 7], 'accept': summ[:, 6]}),
+        'DVR_mcmc': DVR_mcmc, 'k2p_mcmc': k2p_mcmc, 'R1_mcmc': R1_mcmc,
+        'iter': iter_mcmc, 'burn': burn_mcmc, 'y_obs': y_obs, 'km_obs': km_obs,
+        'chains': chains, 'elapsed_time': elapsed,
+    }
+    pickle.dump(save_mcmc_dic, open(fname, 'wb'))
+    with open(fname.replace('.pik', '_summary.csv'), 'w') as f:
+        f.write(diagnostics.summary_csv(DVR_mcmc, R1_mcmc, km_obs['k2p'], summ, ext))
+    diagnostics.append_rhat_log(mcmc_roi_dir, os.path.basename(fname), sample_plot, summ)
+
+
 def main(data_dir=None, prior_path=None, device=0):
     load_km_dir, load_km_fname = find_test_file(data_dir)
     load_test_dict = pickle.load(open(os.path.join(load_km_dir, load_km_fname), 'rb'))
@@ -86,55 +124,71 @@ def main(data_dir=None, prior_path=None, device=0):
     prior_path = prior_path or os.path.join(CUR_DIR, 'prior_stats_nROI{}.pik'.format(n_ROI_test))
     stats_dict = pickle.load(open(prior_path, 'rb'))
     sigma_noise = np.array(load_test_dict['sigma_noise'], dtype=NP_DTYPE)
+    tacref_load = np.array(load_test_dict['vartacref'], dtype=NP_DTYPE)
     str_noise = '_s{:.1e}'.format(mean_sigma_noise_load)
     mcmc_roi_dir = os.path.join(load_km_dir, 'MCMC{}'.format(str_noise))
-    os.makedirs(mcmc_roi_dir, exist_ok=True)
+    rank, world, local, dist_here = _dist_context()
+    if rank == 0:
+        os.makedirs(mcmc_roi_dir, exist_ok=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()                                               # the skip rule below must see one state of the directory
 
     pending = []
     for sample_plot in sample_range:
         km_obs = {'DVR': DVR_load[sample_plot], 'R1': R1_load[sample_plot], 'k2p': k2p_load[sample_plot]}
         fname = os.path.join(mcmc_roi_dir, save_name(km_obs))
         if os.path.isfile(fname):                                   # mcmc.py:125-128
-            print('MCMC File already exists with these parameters (sample {})... Skipping.'.format(sample_plot))
+            if rank == 0:
+                print('MCMC File already exists with these parameters (sample {})... Skipping.'.format(sample_plot))
             continue
         pending.append((sample_plot, km_obs, fname))
+    if world > 1:
+        dist.barrier()                                               # nobody writes before everybody has listed
     if not pending:
+        if dist_here:
+            dist.destroy_process_group()
         return []
 
+    # A chain's Philox stream is keyed by its sample index (mcmc.py:104's loop variable) and its chain index: results do
+    # not depend on which other samples are pending, on batching, or on the number of GPUs.
     idx = [p[0] for p in pending]
     n_store = (iter_mcmc + thin - 1) // thin
     tic = time.time()
-    with MHSampler(n_chains=chains, max_tacs=len(idx), max_draws=n_store, seed=seed, device=device,
-                   tac_gid0=min(idx)) as s:
-        s.set_frames(time_vector, dt)
-        s.set_prior(stats_dict['mu_DVR'], stats_dict['Cov_DVR'], stats_dict['mu_R1'], stats_dict['Cov_R1'])
-        s.set_data(tac_load[idx], np.array(load_test_dict['vartacref'], dtype=NP_DTYPE)[idx], k2p_load[idx, 0], sigma_noise)
-        s.run(draws=iter_mcmc, tune=burn_mcmc, thin=thin)           # pm.sample(draws, tune, step=Metropolis)
-        dvr, r1 = s.chains()
-        summ = s.summary()
-        kernel_ms, launches = s.last_kernel_ms()
-    elapsed_time = time.time() - tic
-    print('elapsed time: {:.1f} sec ({} samples, {} chains; sweep kernels {:.1f} ms)'.format(
-        elapsed_time, len(idx), chains, kernel_ms))
-
     written = []
+    if world == 1:
+        with MHSampler(n_chains=chains, max_tacs=len(idx), max_draws=n_store, seed=seed, device=device) as s:
+            s.set_frames(time_vector, dt)
+            s.set_prior(stats_dict['mu_DVR'], stats_dict['Cov_DVR'], stats_dict['mu_R1'], stats_dict['Cov_R1'])
+            s.set_data(tac_load[idx], tacref_load[idx], k2p_load[idx, 0], sigma_noise)
+            s.set_global_ids(np.asarray(idx, np.uint64))
+            s.run(draws=iter_mcmc, tune=burn_mcmc, thin=thin)       # pm.sample(draws, tune, step=Metropolis)
+            dvr, r1 = s.chains()
+            summ = s.summary()
+            ext = s.summary_ext() if s.n_stored >= 8 else None
+            kernel_ms, launches = s.last_kernel_ms()
+        mine = {j: dict(dvr=dvr[j], r1=r1[j], ext=None if ext is None else ext[j]) for j in range(len(idx))}
+    else:
+        from .distributed import run_sharded
+        summ_t, mine = run_sharded(tac_load[idx], tacref_load[idx], k2p_load[idx, 0], sigma_noise, time_vector, dt, stats_dict,
+                                   draws=iter_mcmc, tune=burn_mcmc, n_chains=chains, thin=thin, seed=seed, max_draws=n_store,
+                                   device=local, tac_ids=idx, keep_chains=True)
+        summ = summ_t.cpu().numpy()
+        kernel_ms = mine.pop('_kernel_ms', 0.0)
+    elapsed_time = time.time() - tic
+    print('elapsed time: {:.1f} sec ({} samples, {} chains, {} GPU(s); sweep kernels of rank {} {:.1f} ms)'.format(
+        elapsed_time, len(idx), chains, world, rank, kernel_ms))
     for j, (sample_plot, km_obs, fname) in enumerate(pending):
-        DVR_mcmc = dvr[j].astype(NP_DTYPE)
-        R1_mcmc = r1[j].astype(NP_DTYPE)
-        k2p_mcmc = np.full(DVR_mcmc.shape[:2], km_obs['k2p'][0])
-        y_obs = tac_load[sample_plot].reshape([n_ROI_test, -1])
-        save_mcmc_dic = {
-            'idata': diagnostics.make_idata(DVR_mcmc, R1_mcmc, km_obs['k2p'],
-                                            {'scaling': summ[j][:, 7], 'accept': summ[j][:, 6]}),
-            'DVR_mcmc': DVR_mcmc, 'k2p_mcmc': k2p_mcmc, 'R1_mcmc': R1_mcmc,
-            'iter': iter_mcmc, 'burn': burn_mcmc, 'y_obs': y_obs, 'km_obs': km_obs,
-            'chains': chains, 'elapsed_time': elapsed_time / len(idx),
-        }
-        pickle.dump(save_mcmc_dic, open(fname, 'wb'))
-        with open(fname.replace('.pik', '_summary.csv'), 'w') as f:
-            f.write(diagnostics.summary_csv(DVR_mcmc, R1_mcmc, km_obs['k2p'], summ[j]))
-        diagnostics.append_rhat_log(mcmc_roi_dir, os.path.basename(fname), sample_plot, summ[j])
+        if j not in mine:
+            continue                                                 # another rank owns this sample
+        m = mine[j]
+        _write_sample(mcmc_roi_dir, fname, sample_plot, km_obs, m['dvr'], m['r1'], tac_load[sample_plot].reshape([n_ROI_test, -1]),
+                      summ[j], m['ext'], elapsed_time / len(idx))
         written.append(fname)
+    if world > 1:
+        dist.barrier()
+        if dist_here:
+            dist.destroy_process_group()
     return written
 
 

@@ -113,8 +113,10 @@ class MHSampler:
         sn = np.ascontiguousarray(sigma_noise, np.float64)
         if mu.shape != (N_FRAMES,) or cov.shape != (N_FRAMES, N_FRAMES) or sn.shape != (N_ROI, N_FRAMES):
             raise ValueError("mu_tac_ref (54,), Cov_tac_ref (54,54), sigma_noise (48,54) expected")
-        self._ck(_lib.lib.petmh_synth(self._h, int(n_tac), int(seed), _d(mu), _d(cov), float(k2p), _d(sn)))
-        self.n_tac = int(n_tac)
+        rc = _lib.lib.petmh_synth(self._h, int(n_tac), int(seed), _d(mu), _d(cov), float(k2p), _d(sn))
+        if rc in (0, -6):                 # PETMH_ESYNTH: the data IS bound, some TACs hit a rejection cap (attempts < 0)
+            self.n_tac = int(n_tac)
+        self._ck(rc)
 
     def synth_get(self):
         """dict(DVR (n,48), R1 (n,48), tac_ref (n,54), tac_clean (n,48,54), y (n,48,54), attempts (n,))."""
@@ -224,6 +226,13 @@ class MHSampler:
         self._ck(_lib.lib.petmh_get_summary(self._h, _f(out)))
         return out
 
+    def summary_ext(self):
+        """(S, 96, 4) float32: hdi_3%, hdi_97%, mcse_sd, ess_sd -- the pm.summary columns beyond summary()'s, from the
+        stored draws on the GPU."""
+        out = np.empty((self.n_tac, N_COORD, 4), np.float32)
+        self._ck(_lib.lib.petmh_get_summary_ext(self._h, _f(out)))
+        return out
+
     def ess_cross_chain(self):
         """(S, 96) float32: tfp.mcmc.effective_sample_size(..., cross_chain_dims=-1) of the stored draws
         (what main_script.py:807-810 computes from DVR_mcmc / R1_mcmc), on the GPU."""
@@ -250,6 +259,28 @@ class MHSampler:
             if a is not None and a.shape != (self.n_tac, self.n_chains, N_COORD):
                 raise ValueError("state arrays must have shape (n_tac, n_chains, 96)")
         self._ck(_lib.lib.petmh_set_state(self._h, None if qq is None else _f(qq), None if ss is None else _f(ss), int(sweep)))
+
+    def checkpoint(self):
+        """Everything needed to continue this run exactly (positions, scalings, tune counters, accepted-move counters,
+        running moments, stored draws, schedule position) as a uint8 array."""
+        n = int(_lib.lib.petmh_checkpoint_bytes(self._h))
+        buf = np.empty(n, np.uint8)
+        self._ck(_lib.lib.petmh_get_checkpoint(self._h, buf.ctypes.data_as(C.c_void_p), n))
+        return buf
+
+    def restore(self, blob):
+        """Continue from a checkpoint() blob (bind the same data with set_data first)."""
+        buf = np.ascontiguousarray(blob, np.uint8)
+        self._ck(_lib.lib.petmh_set_checkpoint(self._h, buf.ctypes.data_as(C.c_void_p), buf.size))
+
+    def set_global_ids(self, tac_gids=None, chain_gid0=0, chains_per_tac_global=0):
+        """Global identity of the local TACs / chains (Philox streams independent of batching and sharding):
+        tac_gids (n_tac,) uint64 or None (= tac_gid0 + local index); chains of a TAC split over ranks pass the
+        first local chain's global index and the global chain count."""
+        g = None if tac_gids is None else np.ascontiguousarray(tac_gids, np.uint64)
+        self._ck(_lib.lib.petmh_set_global_ids(self._h, 0 if g is None else g.size,
+                                               None if g is None else g.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                               int(chain_gid0), int(chains_per_tac_global)))
 
     def set_stream(self, stream):
         self._ck(_lib.lib.petmh_set_stream(self._h, C.c_void_p(int(stream))))

@@ -29,8 +29,36 @@ def test_moments_within_3_mcse_of_oracle(dataset, prior):
              sm[:, 5].max(), sm[:, 3].min()))
     assert np.abs(z_mean).max() < 3.0, "posterior means differ from the oracle by more than 3 MCSE"
     assert np.abs(z_sd).max() < 3.0, "posterior SDs differ from the oracle by more than 3 MCSE"
+    assert np.sqrt((z_mean ** 2).mean()) < 1.4 and np.sqrt((z_sd ** 2).mean()) < 1.4
     assert sm[:, 5].max() < 1.05
     # tuned proposal scales land in the same place (median over chains, factor 1.5)
     sc_gpu = np.median(s.state()[1][0], axis=0)
     sc_ref = np.median(ref["scale"], axis=0)
     assert (np.abs(np.log(sc_gpu / sc_ref)) < np.log(1.6)).all()
+
+
+@pytest.mark.parametrize("sigma,tac", [("0.05", 0), ("0.1", 2), ("0.2", 0), ("0.2", 1)])
+def test_noise_sweep_and_second_tac_within_mcse_of_oracle(prior, sigma, tac):
+    """BASELINE configs[3] noise sweep (sigma 0.05 / 0.2) and a second TAC at 0.1: posterior means and SDs of all 96
+    coordinates against the fp64 C oracle's 16 x 30 000 draws (tools/make_golden_posteriors.py).  Criterion: every
+    |z| < 4 and rms z < 1.4 (z = difference / combined MCSE; 96 correlated z-scores: a max-|z| < 3 rule alone would be
+    a coin flip under a different seed, an rms well above 1 is a real disagreement)."""
+    from pet_posterior_distribution_b200 import MHSampler
+    ref = np.load(os.path.join(GOLDEN, "oracle_posterior_s%s_tac%d.npz" % (sigma, tac)))
+    ds = np.load(os.path.join(GOLDEN, "dataset_s%s.npz" % sigma))
+    s = MHSampler(n_chains=64, max_tacs=1, max_draws=3000, seed=2025)
+    s.set_frames(ds["time_vector"], ds["dt"])
+    s.set_prior(prior["mu_DVR"], prior["Cov_DVR"], prior["mu_R1"], prior["Cov_R1"])
+    y = ds["tac_noisy_sampled"][tac:tac + 1] / ds["dt"][None, None, :]
+    s.set_data(y, ds["vartacref"][tac:tac + 1], ds["vark2p"][tac:tac + 1], ds["sigma_noise"])
+    s.set_global_ids(np.array([tac], np.uint64))
+    s.run(draws=24000, tune=6000, thin=8)
+    sm, ext = s.summary()[0].astype(np.float64), s.summary_ext()[0].astype(np.float64)
+    z_mean = (sm[:, 0] - ref["mean"]) / np.sqrt(sm[:, 2] ** 2 + ref["mcse_mean"] ** 2)
+    z_sd = (sm[:, 1] - ref["sd"]) / np.sqrt(ext[:, 2] ** 2 + ref["mcse_sd"] ** 2)
+    rms = lambda z: float(np.sqrt((z ** 2).mean()))
+    print("sigma %s tac %d: mean max|z| %.2f rms %.2f | sd max|z| %.2f rms %.2f | rhat max %.3f ess_bulk min %.0f"
+          % (sigma, tac, np.abs(z_mean).max(), rms(z_mean), np.abs(z_sd).max(), rms(z_sd), sm[:, 5].max(), sm[:, 3].min()))
+    assert sm[:, 5].max() < 1.05
+    assert np.abs(z_mean).max() < 4.0 and rms(z_mean) < 1.4
+    assert np.abs(z_sd).max() < 4.0 and rms(z_sd) < 1.4

@@ -91,10 +91,27 @@ def test_shard_bounds_cover_everything():
             assert max(shard_sizes(n, w)) - min(shard_sizes(n, w)) <= 1
 
 
+def test_chain_shards_cover_every_chain_once():
+    """S < world: ranks r % S == t form TAC t's group and split its chains contiguously."""
+    from pet_posterior_distribution_b200.distributed import chain_shards
+    for S, C, W in ((1, 64, 8), (3, 1024, 8), (1, 4, 8), (2, 5, 3), (7, 16, 8)):
+        plan = chain_shards(S, C, W)
+        assert len(plan) == W
+        for t in range(S):
+            grp = [r for r in range(W) if plan[r]["tac"] == t]
+            assert grp == plan[grp[0]]["group"] and all(plan[r]["owner"] == grp[0] for r in grp)
+            cover = []
+            for r in grp:
+                cover += list(range(plan[r]["c_lo"], plan[r]["c_hi"]))
+            assert cover == list(range(C))
+            sizes = [plan[r]["c_hi"] - plan[r]["c_lo"] for r in grp]
+            assert max(sizes) - min(sizes) <= 1
+
+
 _GLOO = r"""
 import os, sys, numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, %r)
-from pet_posterior_distribution_b200.distributed import shard_bounds, gather_summaries
+from pet_posterior_distribution_b200.distributed import shard_bounds, gather_summaries, gather_padded, chain_shards
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo")
 n = 7                                     # 7 TACs over 2 ranks: ragged shards (4 + 3)
@@ -102,6 +119,12 @@ lo, hi = shard_bounds(n, world, rank)
 full = torch.arange(n * 96 * 8, dtype=torch.float32).view(n, 96, 8)
 got = gather_summaries(full[lo:hi].clone(), n)
 assert torch.equal(got, full), "rank %%d: gathered summaries differ" %% rank
+# chain-sharded regime: 1 TAC x 5 chains over 2 ranks (3 + 2): the owner reassembles every chain's draws in order
+plan = chain_shards(1, 5, world)
+me = plan[rank]
+draws = torch.arange(5 * 4 * 96, dtype=torch.float32).view(5, 4, 96)
+parts = gather_padded(draws[me["c_lo"]:me["c_hi"]].clone(), [p["c_hi"] - p["c_lo"] for p in plan])
+assert torch.equal(torch.cat([parts[r] for r in me["group"]]), draws), "rank %%d: gathered draws differ" %% rank
 dist.destroy_process_group()
 print("ok", rank)
 """
