@@ -8,8 +8,13 @@ Metric: MH chain-steps/s (chain-step = one scalar coordinate Metropolis update =
 one 54-frame SRTM2 forward model + truncated-normal log-likelihood, one accept/reject;
 one pymc draw = 96 chain-steps).  Workload: BASELINE.json configs[4] ("throughput scaling"),
 sharded by TAC: --tacs-per-gpu TACs x 16 chains x 48 ROIs per GPU (131072 TACs/GPU = the
-config's 1M TACs at 8 GPUs); a step = --sweeps sweeps of every chain in the draw phase
-(scales tuned beforehand), running split-half moments on, no draw storage.
+config's 1M TACs at 8 GPUs; weak scaling, the default) or, with --strong, --total-tacs TACs
+divided over the GPUs (1M TACs on one GPU fit its 180 GB: 104 KB per TAC); a step = --sweeps
+sweeps of every chain in the draw phase, after --tune tuning sweeps (5000: PyMC's scaling table
+has settled, acceptance 0.3-0.35 -- the slower, honest state), running split-half moments on,
+no draw storage.  The end-to-end leg adds, per step, the pinned H2D of the inputs, the summary
+kernel, the NCCL all-gather of every rank's (S, 96, 8) summary rows (written by K3 straight into
+the gather slot) and the D2H of the local rows.
 """
 import argparse
 import json
@@ -162,6 +167,43 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------
+def _ncu_dram_traffic(S, SW, launch_ms):
+    """roofline.traffic = dram__bytes_read.sum + dram__bytes_write.sum of ONE mh_sweep_kernel launch of the default
+    workload, from the ncu capture of this round's kernel committed under profiles/ (tools/capture_bench_dram.sh).  Used
+    only if the capture is of the same kernel, the same workload and a launch time within 25 % of the one measured now
+    (ncu serialises and runs cold, so the times do not agree exactly); else None."""
+    import csv
+    import glob
+    import re
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_sweep_dram_bench.csv"))):
+        try:
+            rows = [r for r in csv.reader(open(path)) if r]
+            hdr = next(r for r in rows if "Kernel Name" in r)
+            ix = {h: i for i, h in enumerate(hdr)}
+            vals = {}
+            for r in rows[rows.index(hdr) + 1:]:
+                if len(r) <= ix["Metric Value"] or "mh_sweep_kernel" not in r[ix["Kernel Name"]]:
+                    continue
+                v = float(r[ix["Metric Value"]].replace(",", ""))
+                unit = r[ix["Metric Unit"]].lower()
+                scale = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(unit, 1)
+                vals[r[ix["Metric Name"]]] = v * scale
+                vals["grid"] = r[ix["Grid Size"]] if "Grid Size" in ix else ""
+            m = re.search(r"r(\d+)_", os.path.basename(path))
+            if {"dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum"} <= set(vals):
+                best = (int(m.group(1)) if m else 0, path, vals)
+        except Exception:
+            continue
+    if best is None:
+        return None, "no ncu DRAM capture under profiles/"
+    _, path, v = best
+    same_grid = re.sub(r"[^0-9]", "", v["grid"].split(",")[0]) == str(S) if v["grid"] else True
+    ok = same_grid and SW == 100 and abs(v["gpu__time_duration.sum"] / launch_ms - 1) < 0.25
+    note = "%s: mh_sweep_kernel grid %s, %.0f ms under ncu (now %.0f ms)" % (os.path.basename(path), v["grid"], v["gpu__time_duration.sum"], launch_ms)
+    return (int(v["dram__bytes_read.sum"] + v["dram__bytes_write.sum"]) if ok else None), note
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -186,7 +228,8 @@ def run_b200(args):
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
-    S, C, SW = args.tacs_per_gpu, N_CHAINS, args.sweeps
+    S = (args.total_tacs // world) if args.strong else args.tacs_per_gpu
+    C, SW = N_CHAINS, args.sweeps
 
     # ---- synthetic inputs: S unique training-style TACs per rank, generated on the GPU (K4) ------------------
     prior = gen.load_prior()
@@ -236,44 +279,79 @@ def run_b200(args):
     wall = time.perf_counter() - t0
     stop.set()
     # ---- timed: the same steps end to end through the public API with HOST buffers --------
-    for _ in range(1):
-        s.set_data_ptr(S, y_pin.data_ptr(), c_pin.data_ptr(), k_pin.data_ptr(), None); s.advance(SW); s.summary_ptr(out_pin.data_ptr())
+    # per step: H2D of the step's inputs (pinned) -> sweeps -> K3 summary written into this rank's slot of the gather buffer
+    # -> NCCL all-gather of every rank's rows (the path's one collective; world 1: none) -> D2H of the local rows (pinned)
+    gather = torch.zeros((world, S, 96, 8), dtype=torch.float32, device="cuda")
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    stream = torch.cuda.current_stream()
+    gather_ms = []
+
+    def e2e_step(timed):
+        s.set_data_ptr(S, y_pin.data_ptr(), c_pin.data_ptr(), k_pin.data_ptr(), None)
+        s.advance(SW)
+        s.summary_into(gather[rank].data_ptr(), stream.cuda_stream)
+        if world > 1:
+            ev[0].record(stream)
+            dist.all_gather_into_tensor(gather.view(world * S, 96, 8), gather[rank])     # in place: the rank's slot is the input
+            ev[1].record(stream)
+        out_pin.copy_(gather[rank], non_blocking=True)
+        stream.synchronize()
+        if world > 1 and timed:
+            gather_ms.append(ev[0].elapsed_time(ev[1]))
+
+    e2e_step(False)
     barrier()
     t1 = time.perf_counter()
     for _ in range(args.steps):
-        s.set_data_ptr(S, y_pin.data_ptr(), c_pin.data_ptr(), k_pin.data_ptr(), None)   # H2D of the step's inputs (pinned)
-        s.advance(SW)
-        s.summary_ptr(out_pin.data_ptr())                                                 # D2H of the step's result (pinned)
+        e2e_step(True)
     barrier()
     e2e_wall = time.perf_counter() - t1
     summ = out_pin.numpy()
     ok = bool(np.isfinite(summ[..., 0]).all() and np.isfinite(summ[..., 1]).all())
+    if world > 1:    # every rank holds every rank's rows: spot-check one remote row block against its owner's copy
+        chk = gather[(rank + 1) % world, :4].clone()
+        src = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(src, gather[rank, :4].clone())
+        ok = ok and bool(torch.equal(torch.nan_to_num(chk), torch.nan_to_num(src[(rank + 1) % world])))
+    del gather
 
-    # ---- BASELINE configs[1]: one test TAC, 48 ROIs x 64 chains, full posterior incl. diagnostics (rank 0) ----
+    # ---- sec per 48-ROI posterior, measured at the reference's shipped length (rank 0) -----------------------------
+    # (file name MH_MCMC_nROI48_it2.0e+04_brn4.0e+04: 40 000 tune + 20 000 draws; mcmc.py:58 chains = 4): pm.sample +
+    # pm.summary + the chain arrays of mcmc.py:156-181 = run + rank-normalised diagnostics on the GPU + D2H of the chains.
+    # Also BASELINE configs[1] (one TAC x 64 chains) at the same length.  No extrapolation.
     cfg2 = None
-    if rank == 0:
+    if rank == 0 and not args.skip_extras:
         try:
-            n_sw_t, n_sw_d = 4000, 2000
-            with MHSampler(n_chains=64, max_tacs=1, max_draws=n_sw_d, seed=11, device=local) as s2:
-                s2.set_frames(t, dtv)
-                s2.set_prior(prior["mu_DVR"], prior["Cov_DVR"], prior["mu_R1"], prior["Cov_R1"])
-                s2.set_data(yb[:1], cb[:1], k_pin.numpy()[:1], sig)
-                s2.run(draws=50, tune=50)          # untimed warm-up of this path: lazy kernel load, workspace allocation
-                s2.summary()
-                t2 = time.perf_counter()
-                s2.run(draws=n_sw_d, tune=n_sw_t)
-                sm2 = s2.summary()
-                dt2 = time.perf_counter() - t2
-            cfg2 = {"workload": "BASELINE configs[1]: 1 TAC x 48 ROIs x 64 chains, %d tune + %d draws, rank-normalised R-hat/ESS on GPU (after a 100-sweep warm-up run of the same path)" % (n_sw_t, n_sw_d),
-                    "seconds": dt2, "chain_steps_per_s": 64 * 96 * (n_sw_t + n_sw_d) / dt2,
-                    "seconds_extrapolated_to_40000_tune_20000_draws": dt2 * 10.0,
-                    "rhat_max": float(np.nanmax(sm2[0, :, 5])), "ess_bulk_min": float(np.nanmin(sm2[0, :, 3]))}
+            cfg2 = {}
+            for name, nch in (("reference_run_4_chains", 4), ("configs1_64_chains", 64)):
+                n_sw_t, n_sw_d = 40000, 20000
+                with MHSampler(n_chains=nch, max_tacs=1, max_draws=n_sw_d, seed=11, device=local) as s2:
+                    s2.set_frames(t, dtv)
+                    s2.set_prior(prior["mu_DVR"], prior["Cov_DVR"], prior["mu_R1"], prior["Cov_R1"])
+                    s2.set_data(yb[:1], cb[:1], k_pin.numpy()[:1], sig)
+                    s2.run(draws=200, tune=200)        # untimed warm-up of this path: lazy kernel load, workspace allocation
+                    s2.summary()
+                    s2.chains()
+                    t2 = time.perf_counter()
+                    s2.run(draws=n_sw_d, tune=n_sw_t)
+                    t3 = time.perf_counter()
+                    sm2 = s2.summary()
+                    ex2 = s2.summary_ext()
+                    t4 = time.perf_counter()
+                    dv2, _ = s2.chains()
+                    t5 = time.perf_counter()
+                cfg2[name] = {"workload": "1 TAC x 48 ROIs x %d chains, %d tune + %d draws (thin 1), rank-normalised R-hat / ESS / MCSE / hdi on "
+                                          "the GPU, chains copied to the host" % (nch, n_sw_t, n_sw_d),
+                              "seconds": t5 - t2, "seconds_sampling": t3 - t2, "seconds_diagnostics": t4 - t3, "seconds_chains_d2h": t5 - t4,
+                              "chain_steps_per_s": nch * 96 * (n_sw_t + n_sw_d) / (t3 - t2),
+                              "rhat_max": float(np.nanmax(sm2[0, :, 5])), "ess_bulk_min": float(np.nanmin(sm2[0, :, 3])),
+                              "chains_shape": list(dv2.shape), "hdi_finite": bool(np.isfinite(ex2[..., :2]).all())}
         except Exception as e:      # pragma: no cover
             cfg2 = {"error": repr(e)}
 
     # ---- chain storage leg (north star: achieved HBM GB/s of the thinned-chain writes), rank 0 -------------
     store = None
-    if rank == 0:
+    if rank == 0 and not args.skip_extras:
         try:
             S3, D3 = 8192, 64
             with MHSampler(n_chains=C, max_tacs=S3, max_draws=D3, seed=5, device=local) as s3:
@@ -312,8 +390,11 @@ def run_b200(args):
         peak_fp32 = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
         peak_sfu = 148 * 16 * sm_mhz * 1e6
         ach = kern_rate_1gpu * FLOP_ALG / 1e12
+        traffic, traffic_note = _ncu_dram_traffic(S, SW, 1e3 * dev_s / max(launches, 1))
         cpu = None
         try:   # CPU baseline in a clean child process (no CUDA context in the forked workers)
+            if args.skip_extras:
+                raise RuntimeError("--skip-extras")
             def child(mode, sweeps):
                 r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1",
                                     "--ref-sweeps", str(sweeps), "--ref-mode", mode], capture_output=True, text=True, timeout=600,
@@ -329,12 +410,13 @@ def run_b200(args):
         line = {
             "metric": "MH chain-steps/sec (SRTM2 lik)", "value": value, "unit": "chain-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall_s / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic: %d unique SRTM2 TACs per rank generated on the GPU (K4 petmh_synth: restated sample_sim_data.py training-style priors, sigma 0.1)" % S,
             "config": {"workload": "BASELINE configs[4] throughput scaling, TAC-sharded: %d TACs/GPU x %d chains x 48 ROIs "
-                                   "(1M TACs at 8 GPUs); step = %d sweeps (x96 chain-steps) of every chain, draw phase after "
-                                   "%d tuning sweeps (chains whose PyMC scaling has fully settled, 5000+ tuning sweeps, accept more "
-                                   "moves and run ~4 %% slower: more visit-order rounds)" % (S, C, SW, TUNE),
+                                   "(%s); step = %d sweeps (x96 chain-steps) of every chain, draw phase after "
+                                   "%d tuning sweeps (>= 5000: PyMC's scaling table has settled, acceptance 0.3-0.35; with --tune 1000 "
+                                   "fewer moves are accepted and the same kernel runs ~4 %% faster)"
+                                   % (S, C, "strong scaling: %d TACs in total" % args.total_tacs if args.strong else "weak scaling: 1M TACs at 8 GPUs", SW, TUNE),
                        "tacs_per_gpu": S, "chains_per_tac": C, "sweeps_per_step": SW, "chain_steps_per_step": steps_per_step,
                        "l2_policy": "per-step working set (inputs+state %.1f GB) >> 126 MB L2" % ((S * 10588 + S * C * 3500) / 1e9),
                        "sec_per_48roi_posterior_60000_sweeps_amortised": 60000 * 96 * C / (value / world) ,
@@ -342,17 +424,20 @@ def run_b200(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "chain-steps/s", "h2d_bytes_per_step": int(S * (48 * 54 + 54 + 1) * 4) * world,
                     "d2h_bytes_per_step": int(S * 96 * 8 * 4) * world,
-                    "note": "per step: petmh_set_data_f32 from pinned host buffers + petmh_advance + petmh_get_summary to pinned host"},
+                    "allgather_ms_per_step": (float(np.mean(gather_ms)) if gather_ms else 0.0),
+                    "allgather_bytes_per_rank": int(S * 96 * 8 * 4) * world if world > 1 else 0,
+                    "note": "per step: petmh_set_data_f32 from pinned host buffers + petmh_advance + petmh_summary_device into the rank's "
+                            "slot of the gather buffer + NCCL all-gather of every rank's rows (world > 1) + D2H of the local rows to pinned host"},
             "gpu_launches": launches,
             "roofline": {"bound": "fp32", "achieved": ach, "peak": peak_fp32, "unit": "TFLOP/s", "frac": ach / peak_fp32,
-                         # dram__bytes_read+write of one mh_sweep_kernel launch at the default workload
-                         # (131072 TACs x 16 chains, 100 sweeps), ncu capture profiles/r01_ncu_sweep_dram_bench.csv
-                         "traffic": 18610574336 if (S == 131072 and SW == 100) else None,
+                         "traffic": traffic, "traffic_source": traffic_note,
                          "note": "dominant kernel mh_sweep_kernel (%.1f %% of the step by CUDA events on its stream); achieved = "
-                                 "3980 algorithmic FP32 flop/chain-step x per-GPU kernel rate; peak = 148 SM x 128 lanes x 2 x SM clock "
-                                 "under load (nominal formula: MEASURED_PEAKS.json has no FP32 figure); pipe utilisation of the same kernel "
-                                 "in its tuned steady state under ncu (profiles/r01_ncu_sweep_tuned_inlined_summary.txt): FMA pipe 54 %%, "
-                                 "XU/MUFU 42 %%, issue slots 62 %%" % (100 * dev_s / wall_s),
+                                 "3980 ALGORITHMIC FP32 flop/chain-step (BASELINE.md section 4: the exact-operator formulation) x per-GPU "
+                                 "kernel rate; peak = 148 SM x 128 lanes x 2 x SM clock under load (nominal formula: MEASURED_PEAKS.json "
+                                 "has no FP32 figure).  The kernel EXECUTES ~1900 flop (361 FFMA2 + 134 FMUL2 + ~110 scalar FP32) and 102 "
+                                 "MUFU per chain-step (Chebyshev-in-k2a operator): its own pipe utilisation in the settled steady state "
+                                 "under ncu (profiles/r02_ncu_sweep_cheb_summary.txt) is FMA pipe 47 %%, XU/MUFU 32 %%, ALU 34 %%, issue "
+                                 "slots 61 %%" % (100 * dev_s / wall_s),
                          "sfu_frac": kern_rate_1gpu * SFU_ALG / peak_sfu,
                          "kernel_chain_steps_per_s_per_gpu": kern_rate_1gpu},
             "cpu_baseline": cpu,
@@ -370,7 +455,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tacs-per-gpu", type=int, default=131072)
     ap.add_argument("--sweeps", type=int, default=100)
-    ap.add_argument("--tune", type=int, default=1000)
+    ap.add_argument("--tune", type=int, default=5000)
+    ap.add_argument("--skip-extras", action="store_true", help="profiling runs: no posterior / storage / CPU-baseline legs")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: --total-tacs TACs divided over the GPUs")
+    ap.add_argument("--total-tacs", type=int, default=1048576)
     ap.add_argument("--cpu-sweeps", type=int, default=40)
     ap.add_argument("--ref-sweeps", type=int, default=8)
     ap.add_argument("--ref-mode", default="faithful", choices=["faithful", "lean"])

@@ -192,5 +192,25 @@ def main(data_dir=None, prior_path=None, device=0):
     return written
 
 
+def _cli(argv=None):
+    """The reference is configured by editing its module constants (mcmc.py:53-59); the same constants can be given
+    on the command line here (an extension: the reference has no CLI)."""
+    import argparse
+    g = globals()
+    ap = argparse.ArgumentParser(description=__doc__.split("\n")[0])
+    ap.add_argument("--chains", type=int, default=chains)
+    ap.add_argument("--iter", type=int, default=iter_mcmc, dest="iter_mcmc")
+    ap.add_argument("--burn", type=int, default=burn_mcmc, dest="burn_mcmc")
+    ap.add_argument("--thin", type=int, default=thin)
+    ap.add_argument("--seed", type=int, default=seed)
+    ap.add_argument("--samples", type=int, nargs=2, default=[sample_range.start, sample_range.stop], metavar=("FIRST", "STOP"))
+    ap.add_argument("--data-dir", default=None)
+    ap.add_argument("--prior", default=None)
+    a = ap.parse_args(argv)
+    g.update(chains=a.chains, iter_mcmc=a.iter_mcmc, burn_mcmc=a.burn_mcmc, thin=a.thin, seed=a.seed,
+             sample_range=range(a.samples[0], a.samples[1]))
+    return main(data_dir=a.data_dir, prior_path=a.prior)
+
+
 if __name__ == "__main__":
-    main()
+    _cli()
