@@ -530,9 +530,7 @@ __device__ PETMH_EVAL3_INLINE float3 eval3(const int l16, const float d0, const 
         const float4* Ap = reinterpret_cast<const float4*>(sA + (blk == 0 ? 0 : (blk == 1 ? AOFF1 : AOFF2)));
         const int n0 = blk == 0 ? NCH0 : (blk == 1 ? NCH1 : NCH2);
         u64 acc0[NPAIR], acc1[NPAIR], acc2[NPAIR];
-#pragma unroll
-        for (int p = 0; p < NPAIR; p++) acc0[p] = acc1[p] = acc2[p] = 0ull;
-        // ---- acc += A[:, d] * T'_d: columns 2 .. n0-1 (recurrence), then 1, 0 and the c_r column (times R1);
+        // ---- acc = sum_d A[:, d] * T'_d: columns 2 .. n0-1 (recurrence), then 1, 0 and the c_r column (times R1);
         // software-pipelined with two register buffers (ping-pong, no copies); FFMA2 takes the per-item scalar as
         // broadcast operand.
 #define PETMH_PAIR(E, pq, m01)                                                                                   \
@@ -543,6 +541,13 @@ __device__ PETMH_EVAL3_INLINE float3 eval3(const int l16, const float d0, const 
     B##0 = (ptr)[0]; B##1 = (ptr)[1]; B##2 = (ptr)[2]; B##3 = (ptr)[3]; B##4 = *reinterpret_cast<const float2*>((ptr) + 4);
 #define PETMH_FULLCOL(B, E)                                                                                      \
     { PETMH_CH(E, 0, B##0) PETMH_CH(E, 1, B##1) PETMH_CH(E, 2, B##2) PETMH_CH(E, 3, B##3) PETMH_PAIR(E, 8, pack2((B##4).x, (B##4).y)) }
+        // the first column initialises the accumulators (a product instead of zeroing + FMA; 0 + a b == a b exactly)
+#define PETMH_PAIR0(E, pq, m01)                                                                                  \
+    { acc0[pq] = fmul2(m01, pack2(E##0, E##0)); acc1[pq] = fmul2(m01, pack2(E##1, E##1)); acc2[pq] = fmul2(m01, pack2(E##2, E##2)); }
+#define PETMH_CH0(E, v, m)                                                                                       \
+    { PETMH_PAIR0(E, 2 * (v), pack2(m.x, m.y)) PETMH_PAIR0(E, 2 * (v) + 1, pack2(m.z, m.w)) }
+#define PETMH_FIRSTCOL(B, E)                                                                                     \
+    { PETMH_CH0(E, 0, B##0) PETMH_CH0(E, 1, B##1) PETMH_CH0(E, 2, B##2) PETMH_CH0(E, 3, B##3) PETMH_PAIR0(E, 8, pack2((B##4).x, (B##4).y)) }
         {
             float4 ma0, ma1, ma2, ma3, mb0, mb1, mb2, mb3;
             float2 ma4, mb4;
@@ -550,8 +555,17 @@ __device__ PETMH_EVAL3_INLINE float3 eval3(const int l16, const float d0, const 
             float y0 = cs0, y1 = cs1, y2 = cs2;
             float x0 = fmaf(ts0, cs0, -coef0), x1 = fmaf(ts1, cs1, -coef1), x2 = fmaf(ts2, cs2, -coef2);
             PETMH_LOADCOL(ma, Ap)
+            {   // columns 2, 3
+                PETMH_LOADCOL(mb, Ap + (RSTRIDE / 4))
+                y0 = fmaf(ts0, x0, -y0); y1 = fmaf(ts1, x1, -y1); y2 = fmaf(ts2, x2, -y2);
+                PETMH_FIRSTCOL(ma, x)
+                PETMH_LOADCOL(ma, Ap + 2 * (RSTRIDE / 4))
+                x0 = fmaf(ts0, y0, -x0); x1 = fmaf(ts1, y1, -x1); x2 = fmaf(ts2, y2, -x2);
+                PETMH_FULLCOL(mb, y)
+                Ap += 2 * (RSTRIDE / 4);
+            }
 #pragma unroll 1
-            for (int c = 2; c < n0; c += 2) {
+            for (int c = 4; c < n0; c += 2) {
                 PETMH_LOADCOL(mb, Ap + (RSTRIDE / 4))
                 y0 = fmaf(ts0, x0, -y0); y1 = fmaf(ts1, x1, -y1); y2 = fmaf(ts2, x2, -y2);   // T'_{c+1}
                 PETMH_FULLCOL(ma, x)
@@ -566,6 +580,9 @@ __device__ PETMH_EVAL3_INLINE float3 eval3(const int l16, const float d0, const 
             PETMH_FULLCOL(mb, coef)                      // column 0: T'_0 = coef
             PETMH_FULLCOL(ma, a)                         // R1 c_r (kinetic_model.py:157)
         }
+#undef PETMH_FIRSTCOL
+#undef PETMH_CH0
+#undef PETMH_PAIR0
 #undef PETMH_FULLCOL
 #undef PETMH_LOADCOL
 #undef PETMH_CH
@@ -1018,18 +1035,18 @@ __global__ void __launch_bounds__(WIDE == 2 ? 288 : (WIDE == 1 ? 96 * WIDE_MAX_T
                         }
                 }
                 if ((w_lo & w_hi) == 0xffffffffu) break;              // warp-uniform: both chains are done
+                // branch-free (the two chains of the warp finish at different rounds: a branch here diverges and reconverges
+                // every round): a finished chain applies a zero move of coordinate 0, r + P * 0 == r exactly
                 const bool any_win = win != 0xffffffffu;
-                const int wi = (int)(win & 63u);                      // winning coordinate (63 if none)
-                const double dw = dmv[wi];                            // the winner's move (unused garbage if none)
-                if (any_win) {
-                    const double* Pc = Pl + wi * 48;
-                    r[0] = fma(Pc[0], dw, r[0]);
-                    r[1] = fma(Pc[16], dw, r[1]);
-                    r[2] = fma(Pc[32], dw, r[2]);
+                const int wi = any_win ? (int)(win & 63u) : 0;        // winning coordinate
+                const double dw = any_win ? dmv[wi] : 0.0;            // the winner's move
+                const double* Pc = Pl + wi * 48;
+                r[0] = fma(Pc[0], dw, r[0]);
+                r[1] = fma(Pc[16], dw, r[1]);
+                r[2] = fma(Pc[32], dw, r[2]);
 #pragma unroll
-                    for (int s = 0; s < SLOTS; s++)
-                        if (key[s] == win) key[s] = 1u;               // accepted (1 < every live key; 0 = never opened)
-                }
+                for (int s = 0; s < SLOTS; s++)
+                    if (key[s] == win) key[s] = 1u;                   // accepted (1 < every live key; 0 = never opened; win = ~0 matches none)
                 last = any_win ? win : 0xfffffffeu;                   // a finished chain idles
             }
             __syncwarp();                                             // dmv is rewritten by the next block
