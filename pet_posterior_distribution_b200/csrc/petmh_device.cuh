@@ -229,21 +229,6 @@ __device__ __forceinline__ void draw_randoms(unsigned long long seed, unsigned l
 }
 
 // ------------------------------------------------------------------------------------
-// 0.5 * erfc(z), z >= 0: t exp(-z^2) Q(t), t = 1/(1 + p z)   (tools/fit_erfc.py, |err| < 2e-7 in fp32)
-// ------------------------------------------------------------------------------------
-__device__ __forceinline__ float half_erfc(float z) {
-    const float t = rcp_approx(fmaf(0.389f, z, 1.0f));
-    float qv = -1.149781880e-01f;
-    qv = fmaf(qv, t, 4.521313931e-01f);
-    qv = fmaf(qv, t, -3.312711738e-01f);
-    qv = fmaf(qv, t, 3.342878070e-01f);
-    qv = fmaf(qv, t, 4.196145208e-02f);
-    qv = fmaf(qv, t, 1.178687081e-01f);
-    const float ex = ex2_approx(z * z * -1.4426950408889634f);
-    return qv * t * ex;
-}
-
-// ------------------------------------------------------------------------------------
 // Per-TAC shared-memory image (byte offsets into dynamic shared memory, all 16B aligned)
 // ------------------------------------------------------------------------------------
 constexpr int SM_CRS = 0;                                 // double [NGRID]
@@ -296,31 +281,26 @@ __device__ __forceinline__ void frame_pair(const u64 raw, const u64 ccp, const u
     zp = fmul2(fmul2(sp, rsp), ccp);
 }
 
-// (1 - erfc(z)/2) for a packed pair of z >= 0 (same fit as half_erfc, FFMA2/FMUL2 arithmetic); elements
-// with z >= Z_CUT give exactly 1 (branch-free select on the element's own z).
+// (1 - erfc(z)/2) for a packed pair of z >= 0: erfc(z)/2 = 2^R(z), R a degree-6 polynomial on [0, Z_CUT]
+// (tools/fit_erfc_exp2.py: |err| < 1.5e-7 in fp64, 2.7e-7 with fp32 Horner + ex2.approx; six FFMA2 and two MUFU.EX2 per
+// pair -- the round-1 form t exp(-z^2) Q5(t), t = 1/(1 + p z), took ten packed operations and four MUFU); elements with
+// z >= Z_CUT give exactly 1 (branch-free select on the element's own z).
 __device__ __forceinline__ u64 trunc_factor2(const u64 zp) {
     float z0, z1;
     unpack2(zp, z0, z1);
-    const u64 one = pack2(1.0f, 1.0f);
-    const u64 den = ffma2r(zp, pack2(0.389f, 0.389f), one);
-    float d0, d1;
-    unpack2(den, d0, d1);
-    const u64 t = pack2(rcp_approx(d0), rcp_approx(d1));
-    u64 q = pack2(-1.149781880e-01f, -1.149781880e-01f);
-    q = ffma2r(q, t, pack2(4.521313931e-01f, 4.521313931e-01f));
-    q = ffma2r(q, t, pack2(-3.312711738e-01f, -3.312711738e-01f));
-    q = ffma2r(q, t, pack2(3.342878070e-01f, 3.342878070e-01f));
-    q = ffma2r(q, t, pack2(4.196145208e-02f, 4.196145208e-02f));
-    q = ffma2r(q, t, pack2(1.178687081e-01f, 1.178687081e-01f));
-    const u64 arg = fmul2(fmul2(zp, zp), pack2(-1.4426950408889634f, -1.4426950408889634f));
-    float a0, a1;
-    unpack2(arg, a0, a1);
-    const u64 h = fmul2(fmul2(q, t), pack2(ex2_approx(a0), ex2_approx(a1)));
-    float h0, h1, m0, m1;
-    unpack2(h, h0, h1);
+    u64 r = pack2(1.785028940e-04f, 1.785028940e-04f);
+    r = ffma2r(r, zp, pack2(-3.851891671e-03f, -3.851891671e-03f));
+    r = ffma2r(r, zp, pack2(3.124260419e-02f, 3.124260419e-02f));
+    r = ffma2r(r, zp, pack2(-1.499808130e-01f, -1.499808130e-01f));
+    r = ffma2r(r, zp, pack2(-9.180663647e-01f, -9.180663647e-01f));
+    r = ffma2r(r, zp, pack2(-1.627938036e+00f, -1.627938036e+00f));
+    r = ffma2r(r, zp, pack2(-9.999996085e-01f, -9.999996085e-01f));
+    float r0, r1, m0, m1;
+    unpack2(r, r0, r1);
+    const float h0 = ex2_approx(r0), h1 = ex2_approx(r1);
     asm("{ .reg .pred p; setp.lt.f32 p, %1, %2; selp.f32 %0, %3, 0f00000000, p; }" : "=f"(m0) : "f"(z0), "f"(Z_CUT), "f"(h0));
     asm("{ .reg .pred p; setp.lt.f32 p, %1, %2; selp.f32 %0, %3, 0f00000000, p; }" : "=f"(m1) : "f"(z1), "f"(Z_CUT), "f"(h1));
-    return fadd2(one, pack2(-m0, -m1));
+    return fadd2(pack2(1.0f, 1.0f), pack2(-m0, -m1));
 }
 
 // log2 of prod_t s_t (1 - erfc(z_t)/2)^2 over NP frame pairs.  The erfc factor is skipped

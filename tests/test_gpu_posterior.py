@@ -27,9 +27,10 @@ def test_moments_within_3_mcse_of_oracle(dataset, prior):
     print("mean: max|z| %.2f rms %.2f | sd: max|z| %.2f rms %.2f | gpu rhat max %.3f ess_bulk min %.0f"
           % (np.abs(z_mean).max(), np.sqrt((z_mean ** 2).mean()), np.abs(z_sd).max(), np.sqrt((z_sd ** 2).mean()),
              sm[:, 5].max(), sm[:, 3].min()))
-    assert np.abs(z_mean).max() < 3.0, "posterior means differ from the oracle by more than 3 MCSE"
-    assert np.abs(z_sd).max() < 3.0, "posterior SDs differ from the oracle by more than 3 MCSE"
-    assert np.sqrt((z_mean ** 2).mean()) < 1.4 and np.sqrt((z_sd ** 2).mean()) < 1.4
+    # 192 z-scores: max |z| < 3 alone is a coin flip under another seed (or another rounding of the same kernel); an rms
+    # well above 1 or a |z| of 4 is a real disagreement
+    assert np.abs(z_mean).max() < 4.0 and np.sqrt((z_mean ** 2).mean()) < 1.4, "posterior means differ from the oracle beyond their MCSE"
+    assert np.abs(z_sd).max() < 4.0 and np.sqrt((z_sd ** 2).mean()) < 1.4, "posterior SDs differ from the oracle beyond their MCSE"
     assert sm[:, 5].max() < 1.05
     # tuned proposal scales land in the same place (median over chains, factor 1.5)
     sc_gpu = np.median(s.state()[1][0], axis=0)
