@@ -263,6 +263,9 @@ constexpr int K = SLOTS;
 #ifndef PETMH_EVAL3_INLINE
 #define PETMH_EVAL3_INLINE __forceinline__
 #endif
+#ifndef PETMH_PEEL
+#define PETMH_PEEL 1       // item 0's likelihood as its own code instance (no accumulator copies)
+#endif
 #ifndef PETMH_TRIANGLE
 #define PETMH_TRIANGLE 1   // triangle-aware column phases: +2 % measured once the rest of the kernel got leaner
 #endif
@@ -275,10 +278,12 @@ __device__ __forceinline__ void frame_pair(const u64 raw, const u64 ccp, const u
     float s0, s1;
     unpack2(raw, s0, s1);
     sp = raw;
-    const u64 rsp = pack2(rsqrt_approx(s0), rsqrt_approx(s1));
-    const u64 up = fmul2(ffma2r(sp, ccp, nyp), rsp);          // (s - y) / (sig sqrt(2 s))
+    const float r0 = rsqrt_approx(s0), r1 = rsqrt_approx(s1);
+    const u64 up = fmul2(ffma2r(sp, ccp, nyp), pack2(r0, r1)); // (s - y) / (sig sqrt(2 s))
     Gp = ffma2r(up, up, Gp);                                   // (y-s)^2 / (2 s sig^2)
-    zp = fmul2(fmul2(sp, rsp), ccp);
+    // z = sqrt(s) / (sig sqrt2) = up + (y / (sig sqrt2)) / sqrt(s): one FFMA2 (ptxas folds the negation into the operand)
+    // instead of the two products s * rsqrt(s) * cc; z only feeds the erfc vote and factor (absolute accuracy ~1e-7)
+    zp = ffma2r(nyp, pack2(-r0, -r1), up);
 }
 
 // (1 - erfc(z)/2) for a packed pair of z >= 0: erfc(z)/2 = 2^R(z), R a degree-6 polynomial on [0, Z_CUT]
@@ -558,7 +563,17 @@ __device__ PETMH_EVAL3_INLINE float3 eval3(const int l16, const float d0, const 
             PETMH_FULLCOL(ma, cs)                        // column 1: T'_1 = coef s
             PETMH_LOADCOL(ma, Ap + 2 * (RSTRIDE / 4))
             PETMH_FULLCOL(mb, coef)                      // column 0: T'_0 = coef
+#if PETMH_PEEL
+            // R1 c_r (kinetic_model.py:157), item 0 only: items 1 and 2 add it while their accumulators are moved into the
+            // registers the shared likelihood code works on (below)
+#define PETMH_PAIRC(pq, m01) ffma2(acc0[pq], m01, pack2(a0, a0));
+            PETMH_PAIRC(0, pack2(ma0.x, ma0.y)) PETMH_PAIRC(1, pack2(ma0.z, ma0.w)) PETMH_PAIRC(2, pack2(ma1.x, ma1.y))
+            PETMH_PAIRC(3, pack2(ma1.z, ma1.w)) PETMH_PAIRC(4, pack2(ma2.x, ma2.y)) PETMH_PAIRC(5, pack2(ma2.z, ma2.w))
+            PETMH_PAIRC(6, pack2(ma3.x, ma3.y)) PETMH_PAIRC(7, pack2(ma3.z, ma3.w)) PETMH_PAIRC(8, pack2(ma4.x, ma4.y))
+#undef PETMH_PAIRC
+#else
             PETMH_FULLCOL(ma, a)                         // R1 c_r (kinetic_model.py:157)
+#endif
         }
 #undef PETMH_FIRSTCOL
 #undef PETMH_CH0
@@ -567,7 +582,54 @@ __device__ PETMH_EVAL3_INLINE float3 eval3(const int l16, const float d0, const 
 #undef PETMH_LOADCOL
 #undef PETMH_CH
 #undef PETMH_PAIR
-        // ---- likelihood of the block's 18 frames, one item per iteration ----
+        // ---- likelihood of the block's 18 frames, one item at a time ----
+#if PETMH_PEEL
+        // Item 0 runs its own instance of the likelihood code directly on acc0.  Items 1 and 2 share a second instance
+        // that works on `raw`: the last operator column (R1 c_r) is the FFMA2 that moves their accumulators there, so no
+        // register copies are left (a single shared instance copied 90 registers per row block; three instances would
+        // not fit the 32 KB instruction cache).
+        auto hook_out = [&](const int it, const u64 (&t)[NPAIR]) {
+#pragma unroll
+            for (int pq = 0; pq < NPAIR; pq++) {
+                float c0, c1;
+                unpack2(t[pq], c0, c1);
+                tac_out[it * NT + blk * RB + 2 * pq] = c0;
+                tac_out[it * NT + blk * RB + 2 * pq + 1] = c1;
+            }
+        };
+        if (HOOK) hook_out(0, acc0);
+        v0 += block_loglik(acc0, sCc + rowoff0 + blk * RSTRIDE, sYcc + rowoff0 + blk * RSTRIDE);
+#pragma unroll 1
+        for (int it = 1; it < K; it++) {
+            const int rowoff = it == 1 ? rowoff1 : rowoff2;
+            const float ri = it == 1 ? a1 : a2;
+            const u64 rid = pack2(ri, ri);
+            const float4* Cp = Ap + 2 * (RSTRIDE / 4);     // the c_r column of this block
+            u64 raw[NPAIR];
+            u64 cr[NPAIR];
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const float4 m = Cp[v];
+                cr[2 * v] = pack2(m.x, m.y);
+                cr[2 * v + 1] = pack2(m.z, m.w);
+            }
+            {
+                const float2 m = *reinterpret_cast<const float2*>(Cp + 4);
+                cr[8] = pack2(m.x, m.y);
+            }
+            if (it == 1) {
+#pragma unroll
+                for (int pq = 0; pq < NPAIR; pq++) raw[pq] = ffma2r(cr[pq], rid, acc1[pq]);
+            } else {
+#pragma unroll
+                for (int pq = 0; pq < NPAIR; pq++) raw[pq] = ffma2r(cr[pq], rid, acc2[pq]);
+            }
+            if (HOOK) hook_out(it, raw);
+            const float vi = block_loglik(raw, sCc + rowoff + blk * RSTRIDE, sYcc + rowoff + blk * RSTRIDE);
+            v1 += it == 1 ? vi : 0.f;
+            v2 += it == 2 ? vi : 0.f;
+        }
+#else
 #pragma unroll 1
         for (int it = 0; it < K; it++) {   // (fully unrolling this loop was measured slower: code size)
             const int rowoff = it == 0 ? rowoff0 : (it == 1 ? rowoff1 : rowoff2);
@@ -599,6 +661,7 @@ __device__ PETMH_EVAL3_INLINE float3 eval3(const int l16, const float d0, const 
             v1 += it == 1 ? vi : 0.f;
             v2 += it == 2 ? vi : 0.f;
         }
+#endif
     }
     // ---- items outside the Chebyshev range: the exact operator, slot by slot (warp-converged calls: block_loglik
     // votes with the full mask), the result taken by the out-of-range lanes only ----
