@@ -64,7 +64,7 @@ def test_hot_loop_fits_the_instruction_cache_and_uses_the_intended_instructions(
     def count(pat):
         return sum(1 for t in hot if re.search(pat, t))
     assert count(r"\bFFMA2\b") >= 120          # packed fp32x2 FMAs: Chebyshev-operator columns + likelihood
-    assert count(r"\bMUFU\.EX2\b") >= 9 and count(r"\bMUFU\.RSQ\b") >= 18 and count(r"\bMUFU\.RCP\b") >= 8
+    assert count(r"\bMUFU\.EX2\b") >= 9 and count(r"\bMUFU\.RSQ\b") >= 18    # erfc factor 2^R(z); rsqrt of the model TAC
     assert count(r"\bMUFU\.LG2\b") >= 3
     assert count(r"\bLDS\.128\b") >= 20        # broadcast loads of the packed operator / per-ROI rows
     assert count(r"\bDFMA\b") >= 6             # fp64 prior bookkeeping in the rounds
