@@ -68,7 +68,11 @@ int petmh_set_prior(petmh_t* h, const double* mu_dvr48, const double* cov_dvr48x
  *   y[n_tac][48][54]   = tac_noisy_sampled / dt  (mcmc.py:79-80,109)
  *   tac_ref[n_tac][54] = vartacref[sample]       (mcmc.py:133-134)
  *   k2p[n_tac]         = km_obs['k2p'][0]        (mcmc.py:150)
- *   sigma_noise[48][54] shared by all TACs       (mcmc.py:96,153) */
+ *   sigma_noise[48][54] shared by all TACs       (mcmc.py:96,153)
+ * Supported scale: |y| and |tac_ref| finite and <= 1e6 (the reference's data are O(1)); PETMH_EINVAL otherwise.  The fp32
+ * likelihood takes one logarithm of the product of four frames' model values, so model TACs must stay within about
+ * [3e-10, 4e9]: states that leave it evaluate to a non-finite log-likelihood and are rejected, as the reference rejects
+ * non-finite log-probabilities -- rescale the activity units if the data themselves are outside. */
 int petmh_set_data(petmh_t* h, int n_tac, const double* y, const double* tac_ref,
                    const double* k2p, const double* sigma_noise);
 /* Global identity of the local TACs and chains, so that Philox streams -- and therefore every draw -- do not depend on

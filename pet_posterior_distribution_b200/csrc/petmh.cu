@@ -367,6 +367,26 @@ extern "C" int petmh_set_prior(petmh_t* h, const double* mu_dvr, const double* c
     return PETMH_OK;
 }
 
+// Supported scale of the inputs (documented in include/petmh.h): |y| and |c_r| at most 1e6 (the reference's data are O(1):
+// activity concentration divided by the frame duration).  Checked on the device: one pass over the batch.
+static int check_data_range(petmh_t* h, int n_tac) {
+    unsigned* d = reinterpret_cast<unsigned*>(h->d_scratch);
+    CU(cudaMemsetAsync(d, 0, 2 * sizeof(unsigned), h->stream));
+    const size_t ny = (size_t)n_tac * 48 * NT, nc = (size_t)n_tac * NT;
+    data_range_kernel<<<(unsigned)std::min<size_t>(1184, (ny + 255) / 256), 256, 0, h->stream>>>(h->d_y, ny, h->d_cref, nc, d);
+    CU(cudaGetLastError());
+    unsigned r[2];
+    CU(cudaMemcpyAsync(r, d, sizeof r, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    float my, mc;
+    memcpy(&my, &r[0], 4);
+    memcpy(&mc, &r[1], 4);
+    if (!(my <= 1e6f) || !(mc <= 1e6f))
+        return fail(h, PETMH_EINVAL, "input scale not supported: max |y| = %g, max |tac_ref| = %g (must be finite and <= 1e6; the fp32 "
+                    "likelihood multiplies four frames' model values before taking a logarithm -- rescale the activity units)", (double)my, (double)mc);
+    return PETMH_OK;
+}
+
 static int upload_noise(petmh_t* h, const double* sig) {
     std::vector<float> cc(48 * NT);
     for (int r = 0; r < 48; r++) {
@@ -426,6 +446,7 @@ extern "C" int petmh_set_data(petmh_t* h, int n_tac, const double* y, const doub
     CU(cudaFreeAsync(dc, h->stream));
     CU(cudaFreeAsync(dk, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    { int rc = check_data_range(h, n_tac); if (rc) { h->have_data = false; return rc; } }
     h->n_tac = n_tac;
     h->have_data = true;
     return PETMH_OK;
@@ -452,7 +473,7 @@ extern "C" int petmh_set_data_f32(petmh_t* h, int n_tac, const float* y, const f
     convert_data_f32_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, h->stream>>>(dc, h->d_cref, nc);
     CU(cudaGetLastError());
     CU(cudaFreeAsync(dc, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    { int rc = check_data_range(h, n_tac); if (rc) { h->have_data = false; return rc; } }
     h->n_tac = n_tac;
     h->have_data = true;
     return PETMH_OK;

@@ -1305,6 +1305,19 @@ __global__ void init_state_kernel(float* q, float* scale, uint8_t* cnt, uint32_t
     if (i < n_chains_total * 96 * 2 * MOMF) mom[i] = 0.f;
 }
 
+// Largest |y| and |c_r| of a batch (as ordered int bits of non-negative floats): the fp32 likelihood takes one lg2 of the product
+// of four frames' model values (trunc_log2), which is only safe while those stay far inside the fp32 range.
+__global__ void data_range_kernel(const float* y, size_t ny, const double* cref, size_t nc, unsigned* out2) {
+    unsigned my = 0u, mc = 0u;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ny; i += (size_t)gridDim.x * blockDim.x)
+        my = max(my, __float_as_uint(fabsf(y[i])));            // (NaN bits compare larger than every finite value: caught too)
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += (size_t)gridDim.x * blockDim.x)
+        mc = max(mc, __float_as_uint(fabsf((float)cref[i])));
+    my = __reduce_max_sync(0xffffffffu, my);
+    mc = __reduce_max_sync(0xffffffffu, mc);
+    if ((threadIdx.x & 31) == 0) { atomicMax(out2, my); atomicMax(out2 + 1, mc); }
+}
+
 __global__ void convert_data_kernel(const double* y64, const double* cref64, const double* k2p64, float* y, double* cref,
                                     float* k2p, size_t ny, size_t nc, size_t nk) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -27,7 +27,7 @@ from .kinetic_model import SRTM2
 from .sampler import MHSampler
 
 NP_DTYPE = np.float64
-FLAG_PLOT = False            # plots (mcmc.py:198-258) are out of scope
+FLAG_PLOT = False            # mcmc.py:23; True writes the figures of mcmc.py:198-258 (plots.py; needs matplotlib)
 
 # ---- configuration: same names and defaults as mcmc.py:45-59 ---------------------------------
 CUR_DIR = './'
@@ -95,8 +95,8 @@ def _dist_context():
     return dist.get_rank(), dist.get_world_size(), local, here
 
 
-def _write_sample(mcmc_roi_dir, fname, sample_plot, km_obs, dvr, r1, y_obs, summ, ext, elapsed):
-    """The three per-sample outputs of mcmc.py:162-194."""
+def _write_sample(mcmc_roi_dir, fname, sample_plot, km_obs, dvr, r1, y_obs, summ, ext, elapsed, prior_mean=None):
+    """The three per-sample outputs of mcmc.py:162-194 (+ the figures of :198-258 when FLAG_PLOT)."""
     DVR_mcmc = dvr.astype(NP_DTYPE)
     R1_mcmc = r1.astype(NP_DTYPE)
     k2p_mcmc = np.full(DVR_mcmc.shape[:2], km_obs['k2p'][0])
@@ -110,6 +110,9 @@ def _write_sample(mcmc_roi_dir, fname, sample_plot, km_obs, dvr, r1, y_obs, summ
     with open(fname.replace('.pik', '_summary.csv'), 'w') as f:
         f.write(diagnostics.summary_csv(DVR_mcmc, R1_mcmc, km_obs['k2p'], summ, ext))
     diagnostics.append_rhat_log(mcmc_roi_dir, os.path.basename(fname), sample_plot, summ)
+    if FLAG_PLOT:
+        from . import plots
+        plots.plot_sample(fname, {'DVR': DVR_mcmc, 'R1': R1_mcmc}, km_obs, prior_mean)
 
 
 def main(data_dir=None, prior_path=None, device=0):
@@ -183,7 +186,7 @@ def main(data_dir=None, prior_path=None, device=0):
             continue                                                 # another rank owns this sample
         m = mine[j]
         _write_sample(mcmc_roi_dir, fname, sample_plot, km_obs, m['dvr'], m['r1'], tac_load[sample_plot].reshape([n_ROI_test, -1]),
-                      summ[j], m['ext'], elapsed_time / len(idx))
+                      summ[j], m['ext'], elapsed_time / len(idx), {'DVR': stats_dict['mu_DVR'], 'R1': stats_dict['mu_R1']})
         written.append(fname)
     if world > 1:
         dist.barrier()

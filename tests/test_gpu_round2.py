@@ -211,3 +211,18 @@ def test_two_frame_grids_in_one_process(dataset, prior):
     rb = forward.srtm2_tac(dataset["time_vector"] * 1.5, dataset["vartacref"][0], DVR, R1, float(dataset["vark2p"][0])).T
     assert np.abs(fa / ra - 1).max() < 1e-5 and np.abs(fb / rb - 1).max() < 1e-5
     assert np.abs(fa - fb).max() > 1e-3
+
+
+def test_input_scale_is_checked(dataset, prior):
+    """Data far outside the supported units (or non-finite) are refused instead of silently freezing chains."""
+    from pet_posterior_distribution_b200 import PetmhError
+    s = make_sampler(dataset, prior, n_chains=2, tacs=[0])
+    y = dataset["tac_noisy_sampled"][:1] / dataset["dt"][None, None, :]
+    for bad in (y * 1e9, np.where(np.arange(y.size).reshape(y.shape) == 7, np.nan, y)):
+        with pytest.raises(PetmhError) as e:
+            s.set_data(bad, dataset["vartacref"][:1], dataset["vark2p"][:1], dataset["sigma_noise"])
+        assert "scale" in str(e.value)
+        with pytest.raises(PetmhError):
+            s.run(draws=2, tune=2)                      # no data bound after the refusal
+    s.set_data(y.astype(np.float32), dataset["vartacref"][:1].astype(np.float32), dataset["vark2p"][:1], dataset["sigma_noise"].astype(np.float32))
+    s.run(draws=2, tune=2)

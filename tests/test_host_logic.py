@@ -81,6 +81,18 @@ def test_idata_stand_in():
     pickle.loads(pickle.dumps(idata))
 
 
+def test_plots_write_the_reference_file_names(tmp_path):
+    """mcmc.py:198-258 (FLAG_PLOT): four PNGs per sample, named like the reference's."""
+    pytest.importorskip("matplotlib")
+    from pet_posterior_distribution_b200 import plots
+    rng = np.random.default_rng(0)
+    ch = {"DVR": 1 + 0.01 * rng.standard_normal((2, 50, 48)), "R1": 0.8 + 0.01 * rng.standard_normal((2, 50, 48))}
+    km = {"DVR": np.ones(48), "R1": 0.8 * np.ones(48), "k2p": np.array([0.0126])}
+    out = plots.plot_sample(str(tmp_path / "MH_x.pik"), ch, km, {"DVR": np.ones(48), "R1": np.ones(48)}, roi_plot=3)
+    assert [os.path.basename(f) for f in out] == ["MH_x_DVR_ROI3.png", "MH_x_DVR_ROI_all.png", "MH_x_R1_ROI3.png", "MH_x_R1_ROI_all.png"]
+    assert all(os.path.getsize(f) > 1000 for f in out)
+
+
 def test_shard_bounds_cover_everything():
     from pet_posterior_distribution_b200.distributed import shard_bounds, shard_sizes
     for n in (0, 1, 7, 100, 1048576):
