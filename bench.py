@@ -329,8 +329,8 @@ def run_b200(args):
                     s2.set_frames(t, dtv)
                     s2.set_prior(prior["mu_DVR"], prior["Cov_DVR"], prior["mu_R1"], prior["Cov_R1"])
                     s2.set_data(yb[:1], cb[:1], k_pin.numpy()[:1], sig)
-                    s2.run(draws=200, tune=200)        # untimed warm-up of this path: lazy kernel load, workspace allocation
-                    s2.summary()
+                    s2.run(draws=n_sw_d, tune=200)     # untimed warm-up of this path at its real size: lazy kernel load, workspace
+                    s2.summary()                       # allocation (the stream-ordered pool keeps the diagnostics' buffers)
                     s2.chains()
                     t2 = time.perf_counter()
                     s2.run(draws=n_sw_d, tune=n_sw_t)
@@ -434,10 +434,10 @@ def run_b200(args):
                          "note": "dominant kernel mh_sweep_kernel (%.1f %% of the step by CUDA events on its stream); achieved = "
                                  "3980 ALGORITHMIC FP32 flop/chain-step (BASELINE.md section 4: the exact-operator formulation) x per-GPU "
                                  "kernel rate; peak = 148 SM x 128 lanes x 2 x SM clock under load (nominal formula: MEASURED_PEAKS.json "
-                                 "has no FP32 figure).  The kernel EXECUTES ~1900 flop (361 FFMA2 + 134 FMUL2 + ~110 scalar FP32) and 102 "
+                                 "has no FP32 figure).  The kernel EXECUTES ~1740 flop (361 FFMA2 + 80 FMUL2 + ~100 scalar FP32) and 89 "
                                  "MUFU per chain-step (Chebyshev-in-k2a operator): its own pipe utilisation in the settled steady state "
-                                 "under ncu (profiles/r02_ncu_sweep_cheb_summary.txt) is FMA pipe 47 %%, XU/MUFU 32 %%, ALU 34 %%, issue "
-                                 "slots 61 %%" % (100 * dev_s / wall_s),
+                                 "under ncu (profiles/r02_ncu_sweep_cheb_summary.txt) is FMA pipe 45 %%, XU/MUFU 31 %%, ALU 30 %%, issue "
+                                 "slots 58 %%" % (100 * dev_s / wall_s),
                          "sfu_frac": kern_rate_1gpu * SFU_ALG / peak_sfu,
                          "kernel_chain_steps_per_s_per_gpu": kern_rate_1gpu},
             "cpu_baseline": cpu,
