@@ -240,7 +240,7 @@ def run_b200(args):
     s.set_frames(t, dtv)
     s.set_prior(prior["mu_DVR"], prior["Cov_DVR"], prior["mu_R1"], prior["Cov_R1"])
     s.synth(S, 4321, prior["mu_tac_ref"], prior["Cov_tac_ref"], float(prior["mu_k2p"]), sig64)
-    g = s.synth_get()                                       # host copies (pinned) for the end-to-end leg
+    g = s.synth_get(fields=("y", "tac_ref"))                # host copies (pinned) for the end-to-end leg
     y_pin = torch.empty((S, 48, 54), dtype=torch.float32, pin_memory=True)
     c_pin = torch.empty((S, 54), dtype=torch.float32, pin_memory=True)
     k_pin = torch.full((S,), float(prior["mu_k2p"]), dtype=torch.float32).pin_memory()

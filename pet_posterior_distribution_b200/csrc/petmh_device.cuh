@@ -264,8 +264,8 @@ constexpr int K = SLOTS;
 #define PETMH_EVAL3_INLINE __forceinline__
 #endif
 #ifndef PETMH_PEEL
-#define PETMH_PEEL 1       // item 0's likelihood as its own code instance (no accumulator copies)
-#endif
+#define PETMH_PEEL 2       // likelihood code instances per row block: 2 = one per item (no accumulator copies; measured best),
+#endif                     // 1 = item 0 peeled + a shared instance for items 1, 2; 0 = one shared instance (round 1)
 #ifndef PETMH_TRIANGLE
 #define PETMH_TRIANGLE 1   // triangle-aware column phases: +2 % measured once the rest of the kernel got leaner
 #endif
@@ -563,7 +563,7 @@ __device__ PETMH_EVAL3_INLINE float3 eval3(const int l16, const float d0, const 
             PETMH_FULLCOL(ma, cs)                        // column 1: T'_1 = coef s
             PETMH_LOADCOL(ma, Ap + 2 * (RSTRIDE / 4))
             PETMH_FULLCOL(mb, coef)                      // column 0: T'_0 = coef
-#if PETMH_PEEL
+#if PETMH_PEEL == 1
             // R1 c_r (kinetic_model.py:157), item 0 only: items 1 and 2 add it while their accumulators are moved into the
             // registers the shared likelihood code works on (below)
 #define PETMH_PAIRC(pq, m01) ffma2(acc0[pq], m01, pack2(a0, a0));
@@ -583,12 +583,7 @@ __device__ PETMH_EVAL3_INLINE float3 eval3(const int l16, const float d0, const 
 #undef PETMH_CH
 #undef PETMH_PAIR
         // ---- likelihood of the block's 18 frames, one item at a time ----
-#if PETMH_PEEL
-        // Item 0 runs its own instance of the likelihood code directly on acc0.  Items 1 and 2 share a second instance
-        // that works on `raw`: the last operator column (R1 c_r) is the FFMA2 that moves their accumulators there, so no
-        // register copies are left (a single shared instance copied 90 registers per row block; three instances would
-        // not fit the 32 KB instruction cache).
-        auto hook_out = [&](const int it, const u64 (&t)[NPAIR]) {
+        auto hook_out = [&](const int it, const u64 (&t)[NPAIR]) {   // parity hook only: the unclamped TAC
 #pragma unroll
             for (int pq = 0; pq < NPAIR; pq++) {
                 float c0, c1;
@@ -597,6 +592,17 @@ __device__ PETMH_EVAL3_INLINE float3 eval3(const int l16, const float d0, const 
                 tac_out[it * NT + blk * RB + 2 * pq + 1] = c1;
             }
         };
+#if PETMH_PEEL == 2
+        // Every item runs its own instance of the likelihood code directly on its accumulators: no register copies, no
+        // reload of the c_r column (hot loop 1 968 instructions = 30.8 KB, just inside the 32 KB instruction cache).
+        if (HOOK) { hook_out(0, acc0); hook_out(1, acc1); hook_out(2, acc2); }
+        v0 += block_loglik(acc0, sCc + rowoff0 + blk * RSTRIDE, sYcc + rowoff0 + blk * RSTRIDE);
+        v1 += block_loglik(acc1, sCc + rowoff1 + blk * RSTRIDE, sYcc + rowoff1 + blk * RSTRIDE);
+        v2 += block_loglik(acc2, sCc + rowoff2 + blk * RSTRIDE, sYcc + rowoff2 + blk * RSTRIDE);
+#elif PETMH_PEEL
+        // Item 0 runs its own instance of the likelihood code directly on acc0.  Items 1 and 2 share a second instance
+        // that works on `raw`: the last operator column (R1 c_r) is the FFMA2 that moves their accumulators there, so no
+        // register copies are left (a single shared instance copied 90 registers per row block).
         if (HOOK) hook_out(0, acc0);
         v0 += block_loglik(acc0, sCc + rowoff0 + blk * RSTRIDE, sYcc + rowoff0 + blk * RSTRIDE);
 #pragma unroll 1

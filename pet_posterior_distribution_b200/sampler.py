@@ -118,16 +118,23 @@ class MHSampler:
             self.n_tac = int(n_tac)
         self._ck(rc)
 
-    def synth_get(self):
-        """dict(DVR (n,48), R1 (n,48), tac_ref (n,54), tac_clean (n,48,54), y (n,48,54), attempts (n,))."""
+    def synth_get(self, fields=("DVR", "R1", "tac_ref", "tac_clean", "y", "attempts")):
+        """dict(DVR (n,48), R1 (n,48), tac_ref (n,54), tac_clean (n,48,54), y (n,48,54), attempts (n,)); `fields` limits
+        what is copied back (a million TACs are 10 GB per (n,48,54) array)."""
         n = self.n_tac
-        dr = np.empty((n, N_COORD), np.float32)
-        cr = np.empty((n, N_FRAMES), np.float64)
-        cl = np.empty((n, N_ROI, N_FRAMES), np.float32)
-        y = np.empty((n, N_ROI, N_FRAMES), np.float32)
-        at = np.empty(n, np.int32)
-        self._ck(_lib.lib.petmh_synth_get(self._h, _f(dr), _d(cr), _f(cl), _f(y), at.ctypes.data_as(C.POINTER(C.c_int))))
-        return dict(DVR=dr[:, :N_ROI].copy(), R1=dr[:, N_ROI:].copy(), tac_ref=cr, tac_clean=cl, y=y, attempts=at)
+        want = set(fields)
+        dr = np.empty((n, N_COORD), np.float32) if want & {"DVR", "R1"} else None
+        cr = np.empty((n, N_FRAMES), np.float64) if "tac_ref" in want else None
+        cl = np.empty((n, N_ROI, N_FRAMES), np.float32) if "tac_clean" in want else None
+        y = np.empty((n, N_ROI, N_FRAMES), np.float32) if "y" in want else None
+        at = np.empty(n, np.int32) if "attempts" in want else None
+        self._ck(_lib.lib.petmh_synth_get(self._h, None if dr is None else _f(dr), None if cr is None else _d(cr),
+                                          None if cl is None else _f(cl), None if y is None else _f(y),
+                                          None if at is None else at.ctypes.data_as(C.POINTER(C.c_int))))
+        out = dict(tac_ref=cr, tac_clean=cl, y=y, attempts=at)
+        if dr is not None:
+            out.update(DVR=dr[:, :N_ROI].copy(), R1=dr[:, N_ROI:].copy())
+        return {k: v for k, v in out.items() if v is not None}
 
     # -- parity hooks ---------------------------------------------------------------------
     def forward(self, tac, DVR, R1):
