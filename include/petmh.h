@@ -145,6 +145,22 @@ int petmh_run_taped(petmh_t* h, int tac, int n_tape_chains, int n_sweeps, int tu
                     const float* normals, const float* logu, const uint8_t* rank,
                     float* draws_out, float* delta_out, uint8_t* accept_out, float* scale_out);
 
+/* ---- the k2-free SRTM as a SAMPLED model ------------------------------------------------------------
+ * kinetic_model.py:62-84 SRTM.forward_model(DVR, k2, R1, tac_ref) with the reference's likelihood block (mcmc.py:151-155),
+ * the handle's MvNormal priors on DVR / R1 (mcmc.py:148-149) and a caller-supplied MvNormal prior on k2[48] (the reference
+ * ships none and mcmc.py never samples k2: this goes beyond it, with pm.Metropolis / CompoundStep semantics over the three
+ * blocks DVR, R1, k2 in that order).  Chains start at the prior means with scaling 1.  Self-contained: uses the handle's
+ * frames / prior / data, leaves its SRTM2 chain state untouched.  A simple kernel (one CTA per chain), not the hot path.
+ *   free run:  tape_* = NULL; draws_out[n_tac][n_chains][ceil(draws/thin)][3][48] f32 (block order DVR, R1, k2);
+ *              accept_rate_out[n_tac][n_chains][3][48] (may be NULL)
+ *   taped run: n_tape_chains chains of TAC tape_tac off tape_normals / tape_logu / tape_rank [c][draws+tune][3][48]
+ *              (f32, f32, u8 visit position); EVERY sweep is recorded: draws_out[c][draws+tune][3][48], optional
+ *              delta_out (f32 log acceptance ratio at decision time) and accept_out (u8). */
+int petmh_srtm_sample(petmh_t* h, const double* mu_k2_48, const double* cov_k2_48x48, int draws, int tune, int thin,
+                      int n_tape_chains, int tape_tac, const float* tape_normals, const float* tape_logu,
+                      const uint8_t* tape_rank, float* draws_out, float* delta_out, uint8_t* accept_out,
+                      float* accept_rate_out);
+
 /* ---- outputs (replaces idata.posterior[...] / pm.summary / pm.rhat mcmc.py:162-187) ---- */
 int petmh_n_stored(const petmh_t* h); /* stored draws per chain so far */
 /* dvr/r1: [n_tac][n_chains][n_stored][48] float32 (DVR_mcmc / R1_mcmc, mcmc.py:162-163) */

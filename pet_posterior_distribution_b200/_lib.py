@@ -57,6 +57,7 @@ def _load():
         "petmh_plan": (C.c_int, [H, C.c_int, C.c_int, C.c_int]),
         "petmh_advance": (C.c_int, [H, C.c_int]),
         "petmh_run_taped": (C.c_int, [H, C.c_int, C.c_int, C.c_int, C.c_int, fp, fp, u8p, fp, fp, u8p, fp]),
+        "petmh_srtm_sample": (C.c_int, [H, dp, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp, fp, u8p, fp, fp, u8p, fp]),
         "petmh_n_stored": (C.c_int, [H]),
         "petmh_get_chains": (C.c_int, [H, fp, fp]),
         "petmh_get_summary": (C.c_int, [H, fp]),

@@ -13,6 +13,7 @@
 #include "petmh_diag.cuh"
 #include "petmh_rankdiag.cuh"
 #include "petmh_synth.cuh"
+#include "petmh_srtm.cuh"
 
 using namespace petmh;
 
@@ -296,6 +297,7 @@ extern "C" int petmh_create(const petmh_cfg* cfg, petmh_t** out) {
     CUC(cudaFuncSetAttribute(synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HOOK_SMEM));
     CUC(cudaFuncSetAttribute(forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HOOK_SMEM));
     CUC(cudaFuncSetAttribute(cheb_operator_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HOOK_SMEM));
+    CUC(cudaFuncSetAttribute(srtm_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HOOK_SMEM));
 #undef CUC
     *out = h;
     return PETMH_OK;
@@ -1101,6 +1103,81 @@ extern "C" int petmh_get_ess_cross_chain(petmh_t* h, float* out) {
     CU(cudaFreeAsync(d_out, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return PETMH_OK;
+}
+
+// ---- the k2-free SRTM as a sampled three-block model ------------------------------------------------
+extern "C" int petmh_srtm_sample(petmh_t* h, const double* mu_k2, const double* cov_k2, int draws, int tune, int thin,
+                                 int n_tape_chains, int tape_tac, const float* tape_normals, const float* tape_logu,
+                                 const uint8_t* tape_rank, float* draws_out, float* delta_out, uint8_t* accept_out,
+                                 float* accept_rate_out) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!mu_k2 || !cov_k2 || !draws_out || draws < 0 || tune < 0 || thin < 1 || draws + tune < 1)
+        return fail(h, PETMH_EINVAL, "bad argument");
+    const bool taped = tape_normals != nullptr;
+    if (taped && (!tape_logu || !tape_rank || n_tape_chains < 1 || tape_tac < 0 || tape_tac >= h->n_tac))
+        return fail(h, PETMH_EINVAL, "bad taped-run arguments");
+    CU(cudaSetDevice(h->cfg.device));
+    std::vector<double> P3(3 * 48 * 48), mu3(3 * 48);
+    memcpy(P3.data(), h->P.data(), 2 * 48 * 48 * sizeof(double));              // DVR, R1 as set by petmh_set_prior
+    memcpy(mu3.data(), h->mu, 2 * 48 * sizeof(double));
+    memcpy(mu3.data() + 96, mu_k2, 48 * sizeof(double));
+    double logdet;
+    if (!spd_inverse(cov_k2, 48, P3.data() + 2 * 48 * 48, &logdet)) return fail(h, PETMH_EINVAL, "k2 prior covariance is not positive definite");
+    const int n_chains = taped ? n_tape_chains : h->cfg.n_chains;
+    const int n_tac = taped ? 1 : h->n_tac;
+    const size_t nc = (size_t)n_tac * n_chains, n = nc * 144;
+    const int total = draws + tune, n_out = taped ? total : (draws + thin - 1) / thin;
+    double *dP = nullptr, *dmu = nullptr;
+    float *dq = nullptr, *dsc = nullptr, *dd = nullptr, *dtn = nullptr, *dtl = nullptr, *ddel = nullptr;
+    int* dcnt = nullptr;
+    unsigned* dna = nullptr;
+    uint8_t *dtr = nullptr, *dacc = nullptr;
+    auto body = [&]() -> int {
+        CU(cudaMalloc(&dP, P3.size() * 8)); CU(cudaMalloc(&dmu, mu3.size() * 8));
+        CU(cudaMalloc(&dq, n * 4)); CU(cudaMalloc(&dsc, n * 4)); CU(cudaMalloc(&dcnt, n * 4)); CU(cudaMalloc(&dna, n * 4));
+        CU(cudaMalloc(&dd, std::max<size_t>(1, nc * (size_t)n_out * 144) * 4));
+        CU(cudaMemcpyAsync(dP, P3.data(), P3.size() * 8, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(dmu, mu3.data(), mu3.size() * 8, cudaMemcpyHostToDevice, h->stream));
+        srtm_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(dq, dsc, dcnt, dna, dmu, n);
+        CU(cudaGetLastError());
+        SrtmParams sp{};
+        sp.P3 = dP; sp.mu3 = dmu; sp.q = dq; sp.scale = dsc; sp.cnt = dcnt; sp.nacc = dna; sp.draws = dd;
+        sp.n_out = n_out; sp.n_chains = n_chains; sp.tune_until = tune; sp.thin = thin;
+        sp.seed = h->cfg.seed; sp.tac_gid0 = h->cfg.tac_gid0;
+        if (taped) {
+            const size_t nt = (size_t)n_chains * total * 144;
+            CU(cudaMalloc(&dtn, nt * 4)); CU(cudaMalloc(&dtl, nt * 4)); CU(cudaMalloc(&dtr, nt));
+            CU(cudaMalloc(&ddel, nt * 4)); CU(cudaMalloc(&dacc, nt));
+            CU(cudaMemcpyAsync(dtn, tape_normals, nt * 4, cudaMemcpyHostToDevice, h->stream));
+            CU(cudaMemcpyAsync(dtl, tape_logu, nt * 4, cudaMemcpyHostToDevice, h->stream));
+            CU(cudaMemcpyAsync(dtr, tape_rank, nt, cudaMemcpyHostToDevice, h->stream));
+            CU(cudaMemsetAsync(ddel, 0, nt * 4, h->stream));
+            CU(cudaMemsetAsync(dacc, 0, nt, h->stream));
+            sp.tape_n = dtn; sp.tape_logu = dtl; sp.tape_rank = dtr; sp.dbg_delta = ddel; sp.dbg_accept = dacc;
+            sp.tape_tac = tape_tac; sp.tape_sweeps = total;
+        }
+        SweepParams p = base_params(h);
+        for (int s0 = 0; s0 < total; s0 += 500) {                                // (chunked: no launch runs for minutes)
+            sp.sweep0 = s0;
+            sp.n_sweeps = std::min(500, total - s0);
+            srtm_sweep_kernel<<<(unsigned)nc, 64, HOOK_SMEM, h->stream>>>(p, sp);
+            CU(cudaGetLastError());
+        }
+        CU(cudaMemcpyAsync(draws_out, dd, nc * (size_t)n_out * 144 * 4, cudaMemcpyDeviceToHost, h->stream));
+        if (taped && delta_out) CU(cudaMemcpyAsync(delta_out, ddel, (size_t)n_chains * total * 144 * 4, cudaMemcpyDeviceToHost, h->stream));
+        if (taped && accept_out) CU(cudaMemcpyAsync(accept_out, dacc, (size_t)n_chains * total * 144, cudaMemcpyDeviceToHost, h->stream));
+        std::vector<unsigned> na(n);
+        CU(cudaMemcpyAsync(na.data(), dna, n * 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if (accept_rate_out)
+            for (size_t i = 0; i < n; i++) accept_rate_out[i] = draws > 0 ? (float)na[i] / (float)draws : 0.f;
+        return PETMH_OK;
+    };
+    rc = body();
+    void* bufs[] = {dP, dmu, dq, dsc, dcnt, dna, dd, dtn, dtl, dtr, ddel, dacc};
+    for (void* b : bufs) if (b) cudaFree(b);
+    return rc;
 }
 
 // ---- K4: synthetic data on the GPU ---------------------------------------------------------

@@ -408,14 +408,15 @@ __device__ __forceinline__ float block_loglik(const u64 (&raw_in)[NPAIR], const 
 // lane, one row block.  Used for items whose R1/DVR is outside the Chebyshev range, and by the parity hooks.
 // HOOK: also write the block's unclamped TAC to tac_item[NT] when `wr`.
 // ------------------------------------------------------------------------------------
-template <bool HOOK>
+// FREE_K2 (the k2-free SRTM of kinetic_model.py:62-84, petmh_srtm.cuh): k2 is a parameter of its own instead of k2p R1.
+template <bool HOOK, bool FREE_K2 = false>
 __device__ __forceinline__ float exact_block(const int roi, const float dv, const float av, const int blk, float* tac_item,
-                                             const bool wr) {
+                                             const bool wr, const float k2_free = 0.f) {
     extern __shared__ __align__(16) unsigned char smem[];
     const float* sM = reinterpret_cast<const float*>(smem + SM_M);
     const float* sCr = reinterpret_cast<const float*>(smem + SM_CR);
     const float k2p = sCr[K2P_SLOT];
-    const float k2 = k2p * av, k2a = k2 / dv;                    // kinetic_model.py:153-154
+    const float k2 = FREE_K2 ? k2_free : k2p * av, k2a = k2 / dv; // kinetic_model.py:153-154 (SRTM: :76-77)
     const float coef = fmaf(-av, k2a, k2);                       // (k2 - R1*k2a), :157
     const float na = k2a * -1.4426950408889634f;                 // exp(-k2a t) = 2^(na t)
     const float* yrow0 = reinterpret_cast<const float*>(smem + SM_YCC) + roi * YS;

@@ -213,6 +213,35 @@ class MHSampler:
                                           _f(draws), _f(delta), acc.ctypes.data_as(u8), _f(scale)))
         return dict(draws=draws, delta=delta, accept=acc.astype(bool), scale=scale)
 
+    def sample_srtm(self, mu_k2, Cov_k2, draws, tune, thin=1, tape=None, tac=0):
+        """The k2-free SRTM (kinetic_model.py:62-84) as a sampled model: element-wise Metropolis over the blocks DVR, R1, k2
+        with an MvNormal(mu_k2, Cov_k2) prior on k2.  Free run: dict(DVR, R1, k2: (S, chains, n, 48),
+        accept_rate (S, chains, 3, 48)).  tape = (normals, logu, rank), each (c, draws + tune, 3, 48): teacher-forcing
+        mode for TAC `tac`: dict(draws (c, s, 3, 48), delta, accept)."""
+        mu = np.ascontiguousarray(mu_k2, np.float64)
+        cov = np.ascontiguousarray(Cov_k2, np.float64)
+        if mu.shape != (N_ROI,) or cov.shape != (N_ROI, N_ROI):
+            raise ValueError("k2 prior must be 48-dimensional")
+        u8 = C.POINTER(C.c_uint8)
+        if tape is None:
+            n_out = (int(draws) + int(thin) - 1) // int(thin)
+            out = np.empty((self.n_tac, self.n_chains, n_out, 3, N_ROI), np.float32)
+            acc = np.empty((self.n_tac, self.n_chains, 3, N_ROI), np.float32)
+            self._ck(_lib.lib.petmh_srtm_sample(self._h, _d(mu), _d(cov), int(draws), int(tune), int(thin), 0, 0, None, None, None,
+                                                _f(out), None, None, _f(acc)))
+            return dict(DVR=out[..., 0, :], R1=out[..., 1, :], k2=out[..., 2, :], accept_rate=acc)
+        n, lu, rk = (np.ascontiguousarray(tape[0], np.float32), np.ascontiguousarray(tape[1], np.float32),
+                     np.ascontiguousarray(tape[2], np.uint8))
+        c, s = n.shape[:2]
+        if s != draws + tune or n.shape != (c, s, 3, N_ROI):
+            raise ValueError("tape arrays must have shape (chains, draws + tune, 3, 48)")
+        out = np.empty((c, s, 3, N_ROI), np.float32)
+        delta = np.empty((c, s, 3, N_ROI), np.float32)
+        acc = np.empty((c, s, 3, N_ROI), np.uint8)
+        self._ck(_lib.lib.petmh_srtm_sample(self._h, _d(mu), _d(cov), int(draws), int(tune), 1, c, int(tac), _f(n), _f(lu),
+                                            rk.ctypes.data_as(u8), _f(out), _f(delta), acc.ctypes.data_as(u8), None))
+        return dict(draws=out, delta=delta, accept=acc.astype(bool))
+
     # -- outputs ------------------------------------------------------------------------------
     @property
     def n_stored(self):
