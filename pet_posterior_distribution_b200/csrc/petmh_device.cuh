@@ -7,14 +7,18 @@
 //
 //  * The reference "continuous convolution" is an exact linear operator conv = M e,
 //    e_f = exp(-k2a t_f), M (54x54, 1122 nnz, 45 active columns) depending only on the
-//    frame grid and the reference-region TAC.  Each CTA builds its TAC's M in shared
-//    memory (fp64 math, fp32 storage) from c_r in the prologue -- M never touches HBM.
+//    frame grid and the reference-region TAC.  On the hot path it is evaluated in a
+//    Chebyshev-in-k2a form, conv = A T(s) with A = M C (54 x {6, 8, 12} columns per row
+//    block) and s the item's scaled k2a: 261 packed FMAs per item, no exponentials; items
+//    whose k2a is outside the expansion's range use M itself (exact_block, cold code).
+//    Each CTA builds its TAC's M and A in shared memory (fp64 math, fp32 storage) from
+//    c_r in the prologue -- neither touches HBM.
 //  * 16 lanes own one chain, each lane 3 ROIs (i = slot*16 + lane16); a warp = 2 chains.
 //    Phase A (expensive, parallel): every lane evaluates forward model + truncated-normal
-//    log-likelihood at its 3 proposals; the 3 items share every broadcast LDS.128 of M
+//    log-likelihood at its 3 proposals; the 3 items share every broadcast LDS.128 of A
 //    (register blocking K=3) and the products run as packed fma.rn.f32x2 (FFMA2).
 //    Phase B (cheap, serial in visit order): prior coupling r = P(q-mu) in fp64,
-//    resolved in "first accepted in visit order" rounds with REDUX.MIN + shuffles.
+//    resolved in "first accepted in visit order" rounds with REDUX.MIN + a broadcast LDS.
 //  * Philox4x32-10 counter-based randoms keyed by (seed; coord, sweep/block, chain gid).
 #pragma once
 #include <cuda_runtime.h>
