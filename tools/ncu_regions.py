@@ -2,6 +2,8 @@
 """Dev tool: per-loop breakdown of an ncu source-page CSV (ncu -i X --page source --csv --print-source sass) of the sweep
 kernel: executed warp-instructions, stall samples and top stall reasons of every loop nest (backward branches) and of the
 straight-line code between them.  Usage: python tools/ncu_regions.py src.csv [min_share_pct]"""
+import signal
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)
 import csv, re, sys, collections
 rows = list(csv.reader(open(sys.argv[1])))
 hdr = rows[1]; ix = {h: i for i, h in enumerate(hdr)}

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Aggregate an ncu source-page CSV (ncu -i X --page source --csv --print-source sass) by
 opcode and by code region: executed warp-instructions and stall samples."""
+import signal
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)
 import csv, collections, sys
 rows = list(csv.reader(open(sys.argv[1])))
 hdr = rows[1]

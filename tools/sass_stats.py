@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Dev tool: static SASS statistics of the sweep kernel's hot loop (size, instruction mix) for a built library.
 Usage: python tools/sass_stats.py [path/to/libpetmh.so]"""
-import collections, re, subprocess, sys
+import collections, re, signal, subprocess, sys
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)
 lib = sys.argv[1] if len(sys.argv) > 1 else "pet_posterior_distribution_b200/libpetmh.so"
 K = "_ZN5petmh15mh_sweep_kernelILi0ELb0ELi0EEEvNS_11SweepParamsE"
 out = subprocess.run(["cuobjdump", "-sass", "-fun", K, lib], capture_output=True, text=True, check=True).stdout
