@@ -30,15 +30,18 @@ PATCHES = [
     ("            if (!TAPED && active) {\n                // one base address per array;",
      "            if (!TAPED && active && PETMH_ABLATE != 2) {\n                // one base address per array;"),
     # x3
-    ("#pragma unroll 1\n        for (int it = 0; it < K; it++) {   // (fully unrolling this loop was measured slower: code size)",
+    ("        v0 += block_loglik(acc0, sCc + rowoff0 + blk * RSTRIDE, sYcc + rowoff0 + blk * RSTRIDE);\n"
+     "        v1 += block_loglik(acc1, sCc + rowoff1 + blk * RSTRIDE, sYcc + rowoff1 + blk * RSTRIDE);\n"
+     "        v2 += block_loglik(acc2, sCc + rowoff2 + blk * RSTRIDE, sYcc + rowoff2 + blk * RSTRIDE);\n",
      "#if PETMH_ABLATE == 3\n        {\n            u64 t0 = 0ull, t1 = 0ull, t2 = 0ull;\n#pragma unroll\n"
      "            for (int pq = 0; pq < NPAIR; pq++) { t0 = fadd2(t0, acc0[pq]); t1 = fadd2(t1, acc1[pq]); t2 = fadd2(t2, acc2[pq]); }\n"
      "            float x, y;\n"
      "            unpack2(t0, x, y); v0 += (x + y) * 1e-3f;\n"
      "            unpack2(t1, x, y); v1 += (x + y) * 1e-3f;\n"
-     "            unpack2(t2, x, y); v2 += (x + y) * 1e-3f;\n        }\n"
-     "#pragma unroll 1\n        for (int it = 0; it < 0; it++) {\n#else\n"
-     "#pragma unroll 1\n        for (int it = 0; it < K; it++) {   // (fully unrolling this loop was measured slower: code size)\n#endif"),
+     "            unpack2(t2, x, y); v2 += (x + y) * 1e-3f;\n        }\n#else\n"
+     "        v0 += block_loglik(acc0, sCc + rowoff0 + blk * RSTRIDE, sYcc + rowoff0 + blk * RSTRIDE);\n"
+     "        v1 += block_loglik(acc1, sCc + rowoff1 + blk * RSTRIDE, sYcc + rowoff1 + blk * RSTRIDE);\n"
+     "        v2 += block_loglik(acc2, sCc + rowoff2 + blk * RSTRIDE, sYcc + rowoff2 + blk * RSTRIDE);\n#endif\n"),
     # x4: skip every operator column but the last (R1 c_r)
     ("            PETMH_LOADCOL(ma, Ap)\n            {   // columns 2, 3",
      "            PETMH_LOADCOL(ma, Ap)\n#if PETMH_ABLATE == 4\n"
@@ -54,8 +57,8 @@ PATCHES = [
     ("    if (__any_sync(0xffffffffu, !(zmin >= Z_CUT))) {   // NaN -> evaluate",
      "    if (PETMH_ABLATE != 7 && __any_sync(0xffffffffu, !(zmin >= Z_CUT))) {"),
     # x9
-    ("    const u64 rsp = pack2(rsqrt_approx(s0), rsqrt_approx(s1));",
-     "    const u64 rsp = PETMH_ABLATE == 9 ? pack2(fmaf(s0, -0.05f, 1.0f), fmaf(s1, -0.05f, 1.0f)) : pack2(rsqrt_approx(s0), rsqrt_approx(s1));"),
+    ("    const float r0 = rsqrt_approx(s0), r1 = rsqrt_approx(s1);",
+     "    const float r0 = PETMH_ABLATE == 9 ? fmaf(s0, -0.05f, 1.0f) : rsqrt_approx(s0), r1 = PETMH_ABLATE == 9 ? fmaf(s1, -0.05f, 1.0f) : rsqrt_approx(s1);"),
     # x11
     ("    uint32_t ci = (uint32_t)i, glo = (uint32_t)gid;\n    asm volatile(\"\" : \"+r\"(ci), \"+r\"(glo));",
      "    uint32_t ci = (uint32_t)i, glo = (uint32_t)gid;\n    asm volatile(\"\" : \"+r\"(ci), \"+r\"(glo));\n"
