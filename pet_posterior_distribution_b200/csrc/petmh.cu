@@ -74,7 +74,6 @@ struct petmh_handle {
     float last_ms = 0.f;
     int last_launches = 0;
     int launch_sweeps = 200;
-    int variant = 0;
     int wide = -1;                // -1 auto, 0 never, 1 always three warps per chain pair, 2 always nine (PETMH_WIDE)
 };
 
@@ -248,7 +247,6 @@ extern "C" int petmh_create(const petmh_cfg* cfg, petmh_t** out) {
     h = new petmh_handle();
     h->cfg = *cfg;
     if (const char* e = getenv("PETMH_LAUNCH_SWEEPS")) h->launch_sweeps = std::max(1, atoi(e));
-    if (const char* e = getenv("PETMH_VARIANT")) h->variant = atoi(e) == 1 ? 1 : 0;
     if (const char* e = getenv("PETMH_WIDE")) h->wide = std::max(0, std::min(2, atoi(e)));
     auto bail = [&](int code) { petmh_destroy(h); return code; };
 #define CUC(call)                                                                                     \
@@ -290,7 +288,6 @@ extern "C" int petmh_create(const petmh_cfg* cfg, petmh_t** out) {
     CUC(cudaMalloc(&h->d_scratch, (48 * NT + 256) * sizeof(float)));
     CUC(cudaMalloc(&h->d_scratch64, NT * NT * sizeof(double)));
     CUC(cudaFuncSetAttribute(mh_sweep_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(256)));
-    CUC(cudaFuncSetAttribute(mh_sweep_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(128)));
     CUC(cudaFuncSetAttribute(mh_sweep_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(256)));
     CUC(cudaFuncSetAttribute(mh_sweep_kernel<0, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_wide()));
     CUC(cudaFuncSetAttribute(mh_sweep_kernel<0, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_wide()));
@@ -672,7 +669,7 @@ static int moments_batch_len(int plan_draws) {
 static int threads_per_cta(const petmh_t* h) {
     int t = h->cfg.n_chains * 16;
     t = (t + 31) / 32 * 32;
-    t = std::min(t, h->variant == 0 ? 256 : 128);
+    t = std::min(t, 256);
     // Jobs of less than one wave (2 CTAs x 148 SMs; e.g. 12 TACs x 256 chains, or one TAC x 64 chains when the wide
     // kernels are off): every CTA is resident at once, so the time is that of the busiest SM -- the sweep loop is
     // latency-bound per warp.  Pick the CTA size (whole warps = chain pairs, any multiple of 32 threads) that minimises
@@ -701,10 +698,8 @@ extern "C" int petmh_advance(petmh_t* h, int n_sweeps) {
     // while every pair gets its own SM, three warps per pair (up to four pairs per CTA) while one wave holds them all
     const size_t pairs = (size_t)h->n_tac * ((h->cfg.n_chains + 1) / 2);
     int wide = 0;
-    if (h->variant == 0) {
-        if (h->wide > 0) wide = h->wide;
-        else if (h->wide < 0) wide = pairs <= 148 ? 2 : (pairs <= (size_t)WIDE_MAX_TRIPLES * 148 ? 1 : 0);
-    }
+    if (h->wide > 0) wide = h->wide;
+    else if (h->wide < 0) wide = pairs <= 148 ? 2 : (pairs <= (size_t)WIDE_MAX_TRIPLES * 148 ? 1 : 0);
     int nthr, chains_per_cta;
     if (wide == 2) {
         nthr = 288;
@@ -762,8 +757,7 @@ extern "C" int petmh_advance(petmh_t* h, int n_sweeps) {
         p.batch_end = b_end;
         if (wide == 2) mh_sweep_kernel<0, false, 2><<<grid, nthr, smem_bytes_wide(), h->stream>>>(p);
         else if (wide) mh_sweep_kernel<0, false, 1><<<grid, nthr, smem_bytes_wide(), h->stream>>>(p);
-        else if (h->variant == 0) mh_sweep_kernel<0, false><<<grid, nthr, smem_bytes(256), h->stream>>>(p);
-        else mh_sweep_kernel<1, false><<<grid, nthr, smem_bytes(128), h->stream>>>(p);
+        else mh_sweep_kernel<0, false><<<grid, nthr, smem_bytes(256), h->stream>>>(p);
         CU(cudaGetLastError());
         if (half >= 0) {
             h->mom_n[half] += n;

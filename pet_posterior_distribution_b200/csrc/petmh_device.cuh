@@ -880,7 +880,8 @@ __device__ __forceinline__ float tune_factor(int c) {
 constexpr int ST_BLOCK = 18, ST_WORDS = 36;
 __host__ __device__ constexpr int smem_bytes(int nthreads) { return SM_STATE + ST_WORDS * 4 * nthreads; }
 
-// VARIANT 0: 256-thread CTAs, 2 CTAs/SM (128-register cap); VARIANT 1: 128-thread CTAs, 3 CTAs/SM (168).
+// VARIANT 0: 256-thread CTAs, 2 CTAs/SM (128-register cap).  (VARIANT 1, 128-thread CTAs at 168 registers, was measured
+// slower in round 1 and is no longer instantiated.)
 // WIDE (small jobs, e.g. one TAC x 64 chains, where a warp's latency and not the GPU's throughput sets the time):
 // warps come in triples; the leader warp (role 0) runs the sweep loop for its two chains exactly as in the normal
 // kernel, but the log-likelihood of ROI slot s is evaluated by the triple's warp s (eval1) -- arguments and results
