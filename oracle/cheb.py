@@ -14,7 +14,7 @@ from scipy.special import iv
 from . import forward
 
 NCOLS = (6, 8, 12)            # petmh_device.cuh NCH0..2
-KT_LO, KT_HI = 0.225, 6.0     # petmh_device.cuh PETMH_CHEB_KT_LO / _HI: range of k2a * t_last
+KT_LO, KT_HI = 0.0, 6.0     # petmh_device.cuh PETMH_CHEB_KT_LO / _HI: range of k2a * t_last
 
 
 def k2a_range(t):

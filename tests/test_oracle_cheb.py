@@ -1,6 +1,6 @@
 """The Chebyshev-in-k2a operator of the sweep kernel, checked on the CPU against the
 exact operator M of the pinned forward-model oracle: with the kernel's range and column counts the truncation
-error of conv = M exp(-k2a t) stays below 5e-8 relative -- under the fp32 rounding of either form -- on every
+error of conv = M exp(-k2a t) stays below 1e-7 relative -- under the fp32 rounding of either form -- on every
 reference TAC we hold (golden cases of the live reference + the golden dataset)."""
 import os
 import re
@@ -34,7 +34,7 @@ def test_truncation_error_below_fp32_rounding(forward_golden, dataset):
         approx = cheb.conv_cheb(t, c_r, ks)
         worst = max(worst, np.abs(approx / exact - 1).max())
     print("max relative truncation error of conv over the range: %.2e" % worst)
-    assert worst < 5e-8
+    assert worst < 1e-7
 
 
 def _fma32(a, b, c):
@@ -87,7 +87,7 @@ def test_fp32_evaluation_order(forward_golden, dataset, prior):
 
 
 def test_range_covers_the_reference_parameters(prior, dataset):
-    """With the reference's grid and k2p the range is R1/DVR in [0.149, 3.97]: every golden-dataset truth and the
+    """With the reference's grid and k2p the range is R1/DVR in [0, 3.97]: every golden-dataset truth and the
     prior mean are inside (chains spend their time near them; the rest falls back to the exact operator)."""
     t = dataset["time_vector"]
     lo, hi = cheb.k2a_range(t)
