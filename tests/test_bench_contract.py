@@ -39,3 +39,17 @@ def test_non_zero_ranks_of_reference_arm_print_nothing():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                        capture_output=True, text=True, timeout=120, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_roofline_traffic_comes_from_the_committed_ncu_capture():
+    """bench.py's roofline.traffic is read from profiles/r*_ncu_sweep_dram_bench.csv (no hard-coded constant) and only
+    when that capture is of the same kernel, workload and (within 25 %) launch time."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    traffic, note = b._ncu_dram_traffic(131072, 100, 1180.0)
+    assert traffic is not None and 1.0e10 < traffic < 3.0e10 and "mh_sweep_kernel" in note
+    assert b._ncu_dram_traffic(131072, 100, 2500.0)[0] is None          # another kernel generation: launch time far off
+    assert b._ncu_dram_traffic(4096, 100, 1180.0)[0] is None            # another workload
+    assert b._ncu_dram_traffic(131072, 50, 1180.0)[0] is None
