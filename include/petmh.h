@@ -97,6 +97,16 @@ int petmh_set_data_f32(petmh_t* h, int n_tac, const float* y, const float* tac_r
  * times: if any TAC exhausts a cap the call returns PETMH_ESYNTH (the data of the other TACs is valid and bound). */
 int petmh_synth(petmh_t* h, int n_tac, uint64_t seed, const double* mu_tacref54, const double* cov_tacref54x54,
                 double k2p, const double* sigma_noise48x54);
+/* Test-style rule of the reference's generator for the following petmh_synth calls (sample_sim_data.py:128-133,
+ * flag_testing_data = True): a drawn vector x of DVR, R1 or the reference TAC is also rejected unless
+ *   0 <= d2 < d2_max,   d2 = (x - mu)^T cov_inv (x - mu),   d2_max = chi2.ppf(alpha, 48)
+ * -- the reference's chi2.cdf(mahalanobis(mu, x, Cov_inv) ** 2, 48) < alpha with dof 48 for all three variables (:132)
+ * and the caller's inverses (the reference: np.linalg.inv(Cov), :106,110,117).  The inverse of the rank-deficient
+ * Cov_tac_ref is numerically indefinite: about half of its forms come out negative, which scipy's mahalanobis turns into
+ * NaN and the reference's comparison rejects; so does this rule.  d2_max <= 0 or a NULL inverse switches it off
+ * (the training-style set, the default). */
+int petmh_synth_set_test_rule(petmh_t* h, double d2_max, const double* cov_inv_dvr48x48, const double* cov_inv_r1_48x48,
+                              const double* cov_inv_tacref54x54);
 /* what petmh_synth generated (any pointer may be NULL): dvr_r1[n][96] f32, tac_ref[n][54] f64,
  * tac_clean[n][48][54] f32 and y[n][48][54] f32 in concentration units, attempts[n] (triples drawn; negative
  * when the TAC hit a rejection cap). */

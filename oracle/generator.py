@@ -17,7 +17,24 @@ def trunc_normal(rng, mean, std, low=0.0, size=None):
     return spst.truncnorm.rvs(a, np.inf, loc=mean, scale=std, size=size, random_state=rng)
 
 
-def truncnormal_samples(rng, mu, cov, cov_inv, n_samples, test_style=False, alpha=0.8, dof=None):
+def mahalanobis_rule(x, mu, cov_inv, dof, alpha, reject_negative=True):
+    """cond_test of sample_sim_data.py:129-133: chi2.cdf(mahalanobis(mu, x, Cov_inv) ** 2, dof) < alpha.
+    scipy's mahalanobis is sqrt(delta @ VI @ delta): where the quadratic form comes out NEGATIVE -- it does for about half
+    of the draws of the reference TAC, whose covariance is rank-deficient (cond ~1e20) and whose np.linalg.inv is numerically
+    indefinite -- the distance is NaN, the cdf is NaN and the comparison is False: the draw is rejected.
+    reject_negative=False is the rule as this oracle had it in round 1 (chi2.cdf of a negative form is 0: accepted); it is
+    kept only so that tools/make_golden*.py reproduce the committed fixtures, which were drawn with it.
+    x: (d,) or (n, d)."""
+    dlt = np.asarray(x, np.float64) - mu
+    m = dlt @ cov_inv @ dlt if dlt.ndim == 1 else np.array([d @ cov_inv @ d for d in dlt])
+    if not reject_negative:
+        return spst.chi2.cdf(m, dof) < alpha
+    with np.errstate(invalid="ignore"):
+        d_square = np.sqrt(m) ** 2
+        return spst.chi2.cdf(d_square, dof) < alpha
+
+
+def truncnormal_samples(rng, mu, cov, cov_inv, n_samples, test_style=False, alpha=0.8, dof=None, reject_negative=True):
     """helper_func.truncnormal_samples (helper_func.py:153-162): rejection until all
     components >= 0 and, for the test set (sample_sim_data.py:128-133), the Mahalanobis
     d^2 satisfies chi2.cdf(d^2, dof) < alpha with dof = len(mu_DVR) = 48 for every
@@ -31,21 +48,19 @@ def truncnormal_samples(rng, mu, cov, cov_inv, n_samples, test_style=False, alph
         x = mu + rng.standard_normal(mu.size) @ A
         if np.any(x < 0):
             continue
-        if test_style:
-            dlt = x - mu
-            if not spst.chi2.cdf(dlt @ cov_inv @ dlt, dof) < alpha:
-                continue
+        if test_style and not mahalanobis_rule(x, mu, cov_inv, dof, alpha, reject_negative):
+            continue
         out.append(x)
     return out
 
 
-def generate(prior, n_samples, mean_sigma_noise=0.1, test_style=False, seed=0, alpha=0.8):
+def generate(prior, n_samples, mean_sigma_noise=0.1, test_style=False, seed=0, alpha=0.8, reject_negative=True):
     """Returns the dict sample_sim_data.py pickles (lists of per-sample arrays)."""
     rng = np.random.default_rng(seed)
     t, dt = frames.frame_grid()
     n_roi = prior["mu_DVR"].size
     inv = {k: np.linalg.inv(prior["Cov_" + k]) for k in ("DVR", "R1", "tac_ref")}
-    kw = dict(test_style=test_style, alpha=alpha, dof=n_roi)
+    kw = dict(test_style=test_style, alpha=alpha, dof=n_roi, reject_negative=reject_negative)
     draw = lambda k, n: truncnormal_samples(rng, prior["mu_" + k], prior["Cov_" + k], inv[k], n, **kw)
     varDVR, varR1, vartacref = draw("DVR", n_samples), draw("R1", n_samples), draw("tac_ref", n_samples)
     k2p = float(prior["mu_k2p"])

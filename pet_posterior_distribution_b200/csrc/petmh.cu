@@ -54,6 +54,8 @@ struct petmh_handle {
     float *d_synth_truth = nullptr, *d_synth_clean = nullptr;
     int* d_synth_attempts = nullptr;
     int* d_synth_capped = nullptr;
+    double* d_synth_cinv = nullptr;  // test-style rule: caller's inverse covariances [48x48 | 48x48 | 54x54]
+    double synth_d2_max = 0.0;       // <= 0: rule off (training-style set)
     // global ids of the Philox streams (petmh_set_global_ids)
     unsigned long long* d_tac_gids = nullptr;
     bool have_tac_gids = false;
@@ -305,7 +307,7 @@ extern "C" void petmh_destroy(petmh_t* h) {
     cudaSetDevice(h->cfg.device);
     void* bufs[] = {h->d_ft, h->d_P, h->d_mu, h->d_cc, h->d_y, h->d_cref, h->d_k2p, h->d_q, h->d_scale,
                     h->d_cnt, h->d_nacc, h->d_mom, h->d_draws, h->d_scratch, h->d_scratch64, h->d_momw, h->d_summary, h->d_summary_ext, h->d_synth_f64, h->d_synth_truth,
-                    h->d_synth_clean, h->d_synth_attempts, h->d_synth_capped, h->d_tac_gids};
+                    h->d_synth_clean, h->d_synth_attempts, h->d_synth_capped, h->d_synth_cinv, h->d_tac_gids};
     for (void* b : bufs) if (b) cudaFree(b);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1211,6 +1213,25 @@ static int psd_factor_T(const double* cov, int n, std::vector<double>& AT) {
     return rank;
 }
 
+extern "C" int petmh_synth_set_test_rule(petmh_t* h, double d2_max, const double* cov_inv_dvr48x48, const double* cov_inv_r1_48x48,
+                                         const double* cov_inv_tacref54x54) {
+    if (!h) return PETMH_EINVAL;
+    if (!(d2_max > 0.0) || !cov_inv_dvr48x48 || !cov_inv_r1_48x48 || !cov_inv_tacref54x54) {   // off: the training-style set
+        h->synth_d2_max = 0.0;
+        return PETMH_OK;
+    }
+    if (!std::isfinite(d2_max)) return fail(h, PETMH_EINVAL, "d2_max must be finite");
+    CU(cudaSetDevice(h->cfg.device));
+    constexpr size_t n48 = 48 * 48, n54 = (size_t)NT * NT;
+    if (!h->d_synth_cinv) CU(cudaMalloc(&h->d_synth_cinv, (2 * n48 + n54) * sizeof(double)));
+    CU(cudaMemcpyAsync(h->d_synth_cinv, cov_inv_dvr48x48, n48 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_synth_cinv + n48, cov_inv_r1_48x48, n48 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_synth_cinv + 2 * n48, cov_inv_tacref54x54, n54 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->synth_d2_max = d2_max;
+    return PETMH_OK;
+}
+
 extern "C" int petmh_synth(petmh_t* h, int n_tac, uint64_t seed, const double* mu_tacref54, const double* cov_tacref54x54,
                            double k2p, const double* sigma_noise48x54) {
     if (!h || !mu_tacref54 || !cov_tacref54x54 || !sigma_noise48x54) return fail(h, PETMH_EINVAL, "null argument");
@@ -1253,6 +1274,10 @@ extern "C" int petmh_synth(petmh_t* h, int n_tac, uint64_t seed, const double* m
     sp.tac_gid0 = h->cfg.tac_gid0;
     sp.tac_gids = h->have_tac_gids ? h->d_tac_gids : nullptr;
     sp.n_capped = h->d_synth_capped;
+    sp.d2_max = h->d_synth_cinv ? h->synth_d2_max : 0.0;
+    sp.cinv[0] = h->d_synth_cinv;
+    sp.cinv[1] = h->d_synth_cinv ? h->d_synth_cinv + 48 * 48 : nullptr;
+    sp.cinv[2] = h->d_synth_cinv ? h->d_synth_cinv + 2 * 48 * 48 : nullptr;
     sp.n_tac = n_tac;
     sp.y = h->d_y; sp.cref = h->d_cref; sp.k2p_out = h->d_k2p;
     sp.truth = h->d_synth_truth; sp.clean = h->d_synth_clean; sp.attempts = h->d_synth_attempts;
@@ -1265,7 +1290,7 @@ extern "C" int petmh_synth(petmh_t* h, int n_tac, uint64_t seed, const double* m
     CU(cudaStreamSynchronize(h->stream));
     h->have_data = true;
     if (capped > 0)
-        return fail(h, PETMH_ESYNTH, "%d of %d synthetic TACs hit a rejection cap (4000 positivity redraws of one vector or 1000 "
+        return fail(h, PETMH_ESYNTH, "%d of %d synthetic TACs hit a rejection cap (4000 positivity / Mahalanobis redraws of one vector or 1000 "
                     "negative-TAC redraws of the triple): their data is not a valid draw; petmh_synth_get's attempts[] is negative "
                     "for them", capped, n_tac);
     return PETMH_OK;

@@ -272,9 +272,6 @@ constexpr int K = SLOTS;
 #ifndef PETMH_PEEL
 #define PETMH_PEEL 2       // likelihood code instances per row block: 2 = one per item (no accumulator copies; measured best),
 #endif                     // 1 = item 0 peeled + a shared instance for items 1, 2; 0 = one shared instance (round 1)
-#ifndef PETMH_TRIANGLE
-#define PETMH_TRIANGLE 1   // triangle-aware column phases: +2 % measured once the rest of the kernel got leaner
-#endif
 
 // Two consecutive frames of one item in packed fp32x2 arithmetic (FMUL2 / FFMA2):
 // TAC assembly (kinetic_model.py:157-158), clamp (mcmc.py:152), Gaussian term, z = sqrt(s)/(sig sqrt2).
@@ -875,9 +872,9 @@ __device__ __forceinline__ float tune_factor(int c) {
 // every access is conflict-free) and only the current block's copy is in registers:
 //   block b (b = 0 DVR, 1 R1), words b*18 + ...: q[3] f32, scale[3] f32, cnt[3] i32,
 //   nacc[3] u32, r[3] f64 (6 words)
-// The running moments of this launch's draw sweeps (sum, sumsq, lag-1 products, previous draw of
-// q - ref, ref = q at launch start) are read-modify-written once per sweep in a global scratch
-// (float4 per coordinate, L2-resident) so that shared memory can hold the fp64 prior precision.
+// The running moments of this launch's draw sweeps (sum and sum of squares of q - ref, ref = q at
+// launch start) are read-modify-written once per sweep in a global scratch (float2 per coordinate,
+// L2-resident) so that shared memory can hold the fp64 prior precision.
 // ------------------------------------------------------------------------------------
 constexpr int ST_BLOCK = 18, ST_WORDS = 36;
 __host__ __device__ constexpr int smem_bytes(int nthreads) { return SM_STATE + ST_WORDS * 4 * nthreads; }
@@ -997,8 +994,7 @@ __global__ void __launch_bounds__(WIDE == 2 ? 288 : (WIDE == 1 ? 96 * WIDE_MAX_T
                 r1 = fma(Pb[j * 48 + 16], dq, r1);
                 r2 = fma(Pb[j * 48 + 32], dq, r2);
             }
-            double* rs = reinterpret_cast<double*>(smem + SM_STATE);   // r words are stored as two floats each
-            (void)rs;
+            // (an r word is stored as two floats)
             ST_F(b * ST_BLOCK + 12) = __int_as_float(__double2loint(r0)); ST_F(b * ST_BLOCK + 13) = __int_as_float(__double2hiint(r0));
             ST_F(b * ST_BLOCK + 14) = __int_as_float(__double2loint(r1)); ST_F(b * ST_BLOCK + 15) = __int_as_float(__double2hiint(r1));
             ST_F(b * ST_BLOCK + 16) = __int_as_float(__double2loint(r2)); ST_F(b * ST_BLOCK + 17) = __int_as_float(__double2hiint(r2));

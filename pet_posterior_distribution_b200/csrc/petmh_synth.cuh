@@ -1,8 +1,8 @@
 // petmh_synth.cuh -- K4: batched synthetic-data generator on the GPU, the step
-// immediately before the hot path.  Restates sample_sim_data.py:141-215 + helper_func.py:146-162 for the
-// training-style set (flag_testing_data = False): per TAC draw DVR, R1 (48) and the reference TAC (54)
-// from the prior MvNormals with positivity rejection, forward-simulate with the exact operator through
-// the production routine (eval3), redraw the triple while any clean TAC value is negative
+// immediately before the hot path.  Restates sample_sim_data.py:128-215 + helper_func.py:146-162: per TAC draw
+// DVR, R1 (48) and the reference TAC (54) from the prior MvNormals with positivity rejection -- and, for the
+// test-style set (flag_testing_data = True, :128-133), the Mahalanobis rule chi2.cdf(d^2, 48) < alpha --,
+// forward-simulate through the production routine (eval3), redraw the triple while any clean TAC value is negative
 // (sample_sim_data.py:171-188), add the signal-dependent truncated-Gaussian noise (:205-215), and leave
 // y = noisy concentration, c_r and k2p in the handle's input buffers -- no host round trip.
 // Distributional, not bitwise, parity with the reference (it uses numpy's global generator).
@@ -21,6 +21,11 @@ struct SynthParams {
     const unsigned long long* tac_gids;   // optional explicit global TAC ids
     int n_tac;
     int* n_capped;           // number of TACs that hit a rejection cap (their data is NOT a valid draw)
+    // test-style rule (sample_sim_data.py:128-133), off when d2_max <= 0: a drawn vector x of variable v is kept only if
+    // 0 <= (x - mu)^T cinv[v] (x - mu) < d2_max = chi2.ppf(alpha, 48) (a negative form is NaN in scipy's mahalanobis and
+    // fails the reference's comparison as well)
+    const double* cinv[3];   // caller-supplied inverses [dim][dim] (the reference: np.linalg.inv(Cov))
+    double d2_max;
     // outputs
     float* y;                // [S][48][54]
     double* cref;            // [S][54]
@@ -44,6 +49,7 @@ __global__ void __launch_bounds__(64) synth_kernel(const SweepParams p, const Sy
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ double z[64];
     __shared__ double xv[3][64];
+    __shared__ double red[2];
     const int tid = threadIdx.x, tac = blockIdx.x;
     const unsigned long long gid = sp.tac_gids ? sp.tac_gids[tac] : sp.tac_gid0 + tac;
     bool capped = false;
@@ -63,9 +69,25 @@ __global__ void __launch_bounds__(64) synth_kernel(const SweepParams p, const Sy
                     for (int k = 0; k < sp.rank[v]; k++) acc = fma(sp.AT[v][k * sp.dim[v] + tid], z[k], acc);
                     xv[v][tid] = acc;
                 }
-                const int neg = __syncthreads_or(tid < sp.dim[v] && acc < 0.0);
+                bool bad = __syncthreads_or(tid < sp.dim[v] && acc < 0.0);   // (the barrier also publishes xv[v])
+                if (!bad && sp.d2_max > 0.0) {                             // CTA-uniform: the Mahalanobis rule of the test set
+                    double part = 0.0;
+                    if (tid < sp.dim[v]) {
+                        const double* ci = sp.cinv[v] + (size_t)tid * sp.dim[v];
+                        double t = 0.0;
+                        for (int j = 0; j < sp.dim[v]; j++) t = fma(ci[j], xv[v][j] - sp.mu3[v][j], t);
+                        part = (acc - sp.mu3[v][tid]) * t;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                    if ((tid & 31) == 0) red[tid >> 5] = part;
+                    __syncthreads();
+                    const double d2 = red[0] + red[1];
+                    bad = !(d2 >= 0.0 && d2 < sp.d2_max);
+                    // (red is rewritten two barriers later at the earliest: no trailing barrier needed)
+                }
                 tries++;
-                if (!neg) break;
+                if (!bad) break;
                 if (tries > 4000) { capped = true; break; }
             }
         }

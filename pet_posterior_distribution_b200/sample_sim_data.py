@@ -35,8 +35,11 @@ def _mvn_positive(rng, mu, cov, cov_inv, n, test_style, alpha_, dof):
         x = mu + rng.standard_normal((max(64, 2 * (n - out.shape[0])), mu.size)) @ A
         ok = (x >= 0).all(axis=1)
         if test_style:
+            # scipy's mahalanobis is sqrt(d' VI d): a NEGATIVE quadratic form (about half of the reference-TAC draws: the
+            # inverse of its rank-deficient covariance is numerically indefinite) is NaN there and fails the test
             d = x - mu
-            ok &= spst.chi2.cdf(np.einsum("ij,jk,ik->i", d, cov_inv, d), dof) < alpha_
+            d2 = np.einsum("ij,jk,ik->i", d, cov_inv, d)
+            ok &= (d2 >= 0) & (spst.chi2.cdf(np.maximum(d2, 0.0), dof) < alpha_)
         out = np.concatenate([out, x[ok]])
     return out[:n]
 
@@ -54,9 +57,10 @@ def noise_table(rng, mean_sigma_noise, t, dt, nroi=48):
     return sigma_roi[:, None] / np.sqrt(dt[None, :] * np.exp(-lam * t))
 
 
-def generate_gpu(prior, n, mean_sigma_noise=0.1, seed=0, device=0, sampler=None):
-    """Training-style set generated entirely on the B200 (K4, petmh_synth): returns the reference's
-    pickle schema.  With `sampler` given, the batch stays bound to it as its data (no host round trip)."""
+def generate_gpu(prior, n, mean_sigma_noise=0.1, seed=0, device=0, sampler=None, test_style=False, alpha_=0.8):
+    """Data set generated entirely on the B200 (K4, petmh_synth): returns the reference's pickle schema.
+    test_style adds the Mahalanobis rule of the reference's test set (sample_sim_data.py:128-133).  With `sampler`
+    given, the batch stays bound to it as its data (no host round trip)."""
     rng = np.random.default_rng(seed)
     t, dt = frame_grid()
     sigma_noise = noise_table(rng, mean_sigma_noise, t, dt)
@@ -65,16 +69,21 @@ def generate_gpu(prior, n, mean_sigma_noise=0.1, seed=0, device=0, sampler=None)
     if own:
         s.set_frames(t, dt)
         s.set_prior(prior["mu_DVR"], prior["Cov_DVR"], prior["mu_R1"], prior["Cov_R1"])
-    s.synth(n, seed, prior["mu_tac_ref"], prior["Cov_tac_ref"], float(prior["mu_k2p"]), sigma_noise)
-    g = s.synth_get()
-    if own:
-        s.close()
+    s.synth_test_rule(alpha_ if test_style else None, prior["Cov_DVR"], prior["Cov_R1"], prior["Cov_tac_ref"])
+    try:
+        s.synth(n, seed, prior["mu_tac_ref"], prior["Cov_tac_ref"], float(prior["mu_k2p"]), sigma_noise)
+        g = s.synth_get()
+    finally:
+        if own:
+            s.close()
+        else:
+            s.synth_test_rule(None)
     return {"varDVR": list(g["DVR"].astype(np.float64)), "varR1": list(g["R1"].astype(np.float64)),
             "vark2p": [prior["mu_k2p"] for _ in range(n)], "vartacref": list(g["tac_ref"]),
             "tac_sampled": list(g["tac_clean"].astype(np.float64) * dt[None, None, :]),
             "tac_noisy_sampled": list(g["y"].astype(np.float64) * dt[None, None, :]),
             "mu_noise": np.zeros_like(sigma_noise), "sigma_noise": sigma_noise, "mean_sigma_noise": mean_sigma_noise,
-            "flag_mahalanobis": False, "target_ROI_names": prior.get("ROI_names"), "time_vector": t, "dt": dt}
+            "flag_mahalanobis": bool(test_style), "target_ROI_names": prior.get("ROI_names"), "time_vector": t, "dt": dt}
 
 
 def generate(prior, n, mean_sigma_noise=0.1, test_style=False, seed=0, device=0, alpha_=0.8):

@@ -118,6 +118,19 @@ class MHSampler:
             self.n_tac = int(n_tac)
         self._ck(rc)
 
+    def synth_test_rule(self, alpha, Cov_DVR=None, Cov_R1=None, Cov_tac_ref=None, dof=N_ROI):
+        """Test-style rejection rule for the following synth() calls (sample_sim_data.py:128-133): keep a drawn vector only
+        if chi2.cdf(Mahalanobis^2, dof) < alpha, with np.linalg.inv(Cov) as the reference computes it (:106,110,117) and
+        dof = 48 for all three variables (:132).  alpha = None switches the rule off (the training-style set)."""
+        if alpha is None:
+            self._ck(_lib.lib.petmh_synth_set_test_rule(self._h, 0.0, None, None, None))
+            return
+        from scipy import stats
+        inv = [np.ascontiguousarray(np.linalg.inv(np.asarray(c, np.float64))) for c in (Cov_DVR, Cov_R1, Cov_tac_ref)]
+        if inv[0].shape != (N_ROI, N_ROI) or inv[1].shape != (N_ROI, N_ROI) or inv[2].shape != (N_FRAMES, N_FRAMES):
+            raise ValueError("Cov_DVR (48,48), Cov_R1 (48,48), Cov_tac_ref (54,54) expected")
+        self._ck(_lib.lib.petmh_synth_set_test_rule(self._h, float(stats.chi2.ppf(alpha, dof)), _d(inv[0]), _d(inv[1]), _d(inv[2])))
+
     def synth_get(self, fields=("DVR", "R1", "tac_ref", "tac_clean", "y", "attempts")):
         """dict(DVR (n,48), R1 (n,48), tac_ref (n,54), tac_clean (n,48,54), y (n,48,54), attempts (n,)); `fields` limits
         what is copied back (a million TACs are 10 GB per (n,48,54) array)."""

@@ -31,3 +31,29 @@ def test_reproducible_and_noise_scales(prior):
     # units: tac_sampled is concentration x dt (sample_sim_data.py:178); y_obs = noisy/dt (mcmc.py:79-80)
     m = generator.model_from_dataset(a, prior, 0)
     assert np.allclose(m.y * a["dt"][None, :], a["tac_noisy_sampled"][0])
+
+
+def test_mahalanobis_rule_matches_scipy(prior):
+    """The test-set rule (sample_sim_data.py:129-133) restated == the reference's own call,
+    chi2.cdf(scipy.spatial.distance.mahalanobis(mu, x, Cov_inv) ** 2, 48) < alpha, including its NaN behaviour: the inverse
+    of the rank-deficient Cov_tac_ref is numerically indefinite, about half of its quadratic forms are negative, sqrt gives
+    NaN and the draw is rejected."""
+    import warnings
+    from scipy import stats
+    from scipy.spatial.distance import mahalanobis
+    rng = np.random.default_rng(0)
+    for k in ("DVR", "R1", "tac_ref"):
+        mu, cov = prior["mu_" + k], prior["Cov_" + k]
+        inv = np.linalg.inv(cov)                                      # sample_sim_data.py:106,110,117
+        _, sv, vt = np.linalg.svd(cov)
+        x = mu + rng.standard_normal((300, mu.size)) @ (np.sqrt(sv)[:, None] * vt)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = np.array([stats.chi2.cdf(mahalanobis(mu, v, inv) ** 2, 48) < 0.8 for v in x])
+        mine = generator.mahalanobis_rule(x, mu, inv, 48, 0.8)
+        if k == "tac_ref":       # rounding noise of an ill-conditioned form: the summation order may flip a rare draw
+            assert (ref == mine).mean() > 0.97 and 0.01 < mine.mean() < 0.25
+            neg = np.einsum("ni,ij,nj->n", x - mu, inv, x - mu) < 0
+            assert neg.mean() > 0.3 and not mine[neg].any()          # negative forms are rejected, as in the reference
+        else:
+            assert (ref == mine).all() and 0.6 < mine.mean() < 0.95

@@ -66,3 +66,56 @@ def test_reproducible_and_shard_independent(prior, dataset):
     assert np.array_equal(c["y"], a["y"][4:]) and np.array_equal(c["DVR"], a["DVR"][4:])
     d = _make(prior, dataset, 8, seed=6).synth_get()
     assert not np.array_equal(d["y"], a["y"])
+
+
+def test_test_style_mahalanobis_rule(prior, dataset):
+    """K4 with the reference's test-set rule (sample_sim_data.py:128-133): every kept DVR / R1 draw satisfies
+    chi2.cdf(d^2, 48) < alpha (recomputed on the host with the same inverse), the rule binds (the training-style stream
+    violates it for ~20 % of the draws), the kept draws are distributed like the host path's, and switching the rule off
+    restores the training-style stream bit for bit."""
+    from scipy import stats
+    from pet_posterior_distribution_b200 import MHSampler
+    from pet_posterior_distribution_b200 import sample_sim_data as gen
+    n, alpha = 768, 0.8
+    thr = stats.chi2.ppf(alpha, 48)
+    s = MHSampler(n_chains=2, max_tacs=n, seed=1)
+    s.set_frames(dataset["time_vector"], dataset["dt"])
+    s.set_prior(prior["mu_DVR"], prior["Cov_DVR"], prior["mu_R1"], prior["Cov_R1"])
+    args = (prior["mu_tac_ref"], prior["Cov_tac_ref"], float(prior["mu_k2p"]), dataset["sigma_noise"])
+    s.synth_test_rule(alpha, prior["Cov_DVR"], prior["Cov_R1"], prior["Cov_tac_ref"])
+    s.synth(n, 7, *args)
+    g = s.synth_get()
+    s.synth_test_rule(None)
+    s.synth(n, 7, *args)
+    tr = s.synth_get()
+
+    def d2(x, k):
+        d = x.astype(np.float64) - prior["mu_" + k]
+        return np.einsum("ni,ij,nj->n", d, np.linalg.inv(prior["Cov_" + k]), d)
+
+    for k in ("DVR", "R1", "tac_ref", "tac_clean", "y"):
+        assert np.isfinite(g[k]).all() and (g[k] >= 0).all(), k
+    assert (g["attempts"] >= 1).all()
+    for k in ("DVR", "R1"):
+        a, b = d2(g[k], k), d2(tr[k], k)
+        assert a.min() >= 0 and a.max() < thr + 0.1, (k, a.max(), thr)   # (+0.1: the draws come back rounded to fp32)
+        assert a.max() > 0.85 * thr                                      # ... and the bound is reached
+        assert 0.08 < (b > thr).mean() < 0.35, (k, (b > thr).mean())     # the rule binds: 1 - alpha of the unfiltered draws
+        assert g[k].std(axis=0).mean() < tr[k].std(axis=0).mean()        # truncation in Mahalanobis distance shrinks the spread
+    # the host path of the same rule (numpy draws, sample_sim_data.generate): same distribution of the kept draws
+    m = 400
+    ref = gen.generate(prior, m, 0.1, test_style=True, seed=5, alpha_=alpha)
+    for key, okey in (("DVR", "varDVR"), ("R1", "varR1")):
+        a, b = g[key].astype(np.float64), np.asarray(ref[okey])
+        se = np.sqrt(a.var(axis=0) / n + b.var(axis=0) / m)
+        assert np.abs((a.mean(axis=0) - b.mean(axis=0)) / se).max() < 5.0, key
+        assert np.abs(a.std(axis=0) / b.std(axis=0) - 1).max() < 0.2, key
+    # rule off again == the training-style generator
+    plain = _make(prior, dataset, n, seed=7).synth_get()
+    assert np.array_equal(plain["y"], tr["y"]) and np.array_equal(plain["DVR"], tr["DVR"])
+    assert not np.array_equal(plain["DVR"], g["DVR"])
+    # the pickle schema of the GPU path carries the flag (sample_sim_data.py:221)
+    ds = gen.generate_gpu(prior, 8, 0.1, seed=3, test_style=True)
+    assert ds["flag_mahalanobis"] is True and len(ds["varDVR"]) == 8 and ds["tac_noisy_sampled"][0].shape == (48, 54)
+    assert gen.generate_gpu(prior, 8, 0.1, seed=3)["flag_mahalanobis"] is False
+    s.close()

@@ -28,7 +28,8 @@ def dataset(sig):
     if not os.path.isfile(path):
         from oracle import generator
         pr = dict(np.load(os.path.join(G, "prior_stats_nROI48.npz")))
-        ds = generator.generate(pr, 2, mean_sigma_noise=float(sig), test_style=True, seed=int(float(sig) * 1000))
+        ds = generator.generate(pr, 2, mean_sigma_noise=float(sig), test_style=True, seed=int(float(sig) * 1000),
+                                reject_negative=False)   # (the fixtures predate the NaN rule of oracle.generator.mahalanobis_rule)
         keep = ("varDVR", "varR1", "vark2p", "vartacref", "tac_sampled", "tac_noisy_sampled", "mu_noise", "sigma_noise",
                 "mean_sigma_noise", "time_vector", "dt", "seed")
         np.savez_compressed(path, **{k: np.asarray(ds[k]) for k in keep})
