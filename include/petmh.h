@@ -88,6 +88,22 @@ int petmh_set_global_ids(petmh_t* h, int n_tac, const uint64_t* tac_gids, uint64
 int petmh_set_data_f32(petmh_t* h, int n_tac, const float* y, const float* tac_ref,
                        const float* k2p, const float* sigma_noise);
 
+/* ---- the module-level helpers of kinetic_model.py, any grid, fp64 (callers of the reference's functions outside mcmc.py;
+ * the sampler itself evaluates the same arithmetic in operator form and never calls these) ----
+ * replaces interp1d_linear_vec(x, xp, fp) kinetic_model.py:35-57 (dim = 0): out[nx][m] = W fp[np][m] with the reference's
+ * weights -- searchsorted-left node hi, lo = hi - 1 (index -1 wraps for x <= xp[0], as numpy's does), |xp[lo] - x| on hi and
+ * |xp[hi] - x| on lo, normalised.  x beyond xp[np-1] is PETMH_EINVAL (the reference raises IndexError). */
+int petmh_interp1d_linear(petmh_t* h, int nx, const double* x, int np, const double* xp, const double* fp, int m, double* out);
+/* replaces estimate_continuous_convolution(x, y0, y1, num_points_resample) kinetic_model.py:12-32 = SRTM.convolve /
+ * SRTM2.convolve (:125-128, :199-201): y0[n] (np.interp) and y1[n][m] (interp1d_linear_vec) resampled onto num_points
+ * (0: the default 2 n) uniform points on [x[0], x[n-1]], causal discrete convolution truncated to that length times the grid
+ * spacing, interpolated back to x: out[n][m].  x strictly increasing. */
+int petmh_continuous_convolution(petmh_t* h, int n, const double* x, const double* y0, const double* y1, int m, int num_points,
+                                 double* out);
+/* replaces SRTM.make_time_exponential(param, time_vector) kinetic_model.py:118-122 (= SRTM2's, :192-196) without the
+ * optional scales: out[nt][np] = exp(param[j] * t[i]). */
+int petmh_time_exponential(petmh_t* h, int np, const double* param, int nt, const double* t, double* out);
+
 /* ---- synthetic inputs on the GPU (K4; replaces sample_sim_data.py:141-215 for the training-style set) ----
  * Draw, per TAC, DVR / R1 from the handle's priors and the reference TAC from N(mu_tacref, cov_tacref)
  * with positivity rejection (helper_func.py:153-162), forward-simulate, redraw while any clean TAC value is

@@ -44,6 +44,9 @@ def _load():
         "petmh_set_data": (C.c_int, [H, C.c_int, dp, dp, dp, dp]),
         "petmh_set_global_ids": (C.c_int, [H, C.c_int, C.POINTER(C.c_uint64), C.c_uint64, C.c_uint64]),
         "petmh_set_data_f32": (C.c_int, [H, C.c_int, fp, fp, fp, fp]),
+        "petmh_interp1d_linear": (C.c_int, [H, C.c_int, dp, C.c_int, dp, dp, C.c_int, dp]),
+        "petmh_continuous_convolution": (C.c_int, [H, C.c_int, dp, dp, dp, C.c_int, C.c_int, dp]),
+        "petmh_time_exponential": (C.c_int, [H, C.c_int, dp, C.c_int, dp, dp]),
         "petmh_synth": (C.c_int, [H, C.c_int, C.c_uint64, dp, dp, C.c_double, dp]),
         "petmh_synth_set_test_rule": (C.c_int, [H, C.c_double, dp, dp, dp]),
         "petmh_synth_get": (C.c_int, [H, fp, dp, fp, fp, C.POINTER(C.c_int)]),

@@ -14,6 +14,7 @@
 #include "petmh_rankdiag.cuh"
 #include "petmh_synth.cuh"
 #include "petmh_srtm.cuh"
+#include "petmh_conv.cuh"
 
 using namespace petmh;
 
@@ -95,7 +96,27 @@ static int fail(petmh_t* h, int code, const char* fmt, ...) {
             return fail(h, PETMH_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-extern "C" int petmh_version(void) { return 100; }
+// stream-ordered device buffer, released on every exit path (the CU() macro returns from the middle of a function)
+template <class T>
+struct Staged {
+    T* p = nullptr;
+    cudaStream_t st = nullptr;
+    Staged() = default;
+    Staged(const Staged&) = delete;
+    Staged& operator=(const Staged&) = delete;
+    ~Staged() { if (p) cudaFreeAsync(p, st); }
+    cudaError_t alloc(size_t n, cudaStream_t s) {
+        st = s;
+        return cudaMallocAsync(&p, std::max<size_t>(n, 1) * sizeof(T), s);
+    }
+    cudaError_t upload(const T* src, size_t n, cudaStream_t s) {
+        const cudaError_t e = alloc(n, s);
+        return e != cudaSuccess ? e : cudaMemcpyAsync(p, src, n * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+};
+using StagedF64 = Staged<double>;
+
+extern "C" int petmh_version(void) { return 101; }
 
 extern "C" const char* petmh_last_error(const petmh_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
@@ -434,18 +455,14 @@ extern "C" int petmh_set_data(petmh_t* h, int n_tac, const double* y, const doub
     if (sigma_noise) { int rc = upload_noise(h, sigma_noise); if (rc) return rc; }
     if (!h->have_noise) return fail(h, PETMH_EINVAL, "sigma_noise never set");
     const size_t ny = (size_t)n_tac * 48 * NT, nc = (size_t)n_tac * NT, nk = n_tac;
-    double *dy = nullptr, *dc = nullptr, *dk = nullptr;
-    CU(cudaMallocAsync(&dy, ny * sizeof(double), h->stream));
-    CU(cudaMallocAsync(&dc, nc * sizeof(double), h->stream));
-    CU(cudaMallocAsync(&dk, nk * sizeof(double), h->stream));
-    CU(cudaMemcpyAsync(dy, y, ny * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(dc, tac_ref, nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(dk, k2p, nk * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    convert_data_kernel<<<(unsigned)((ny + 255) / 256), 256, 0, h->stream>>>(dy, dc, dk, h->d_y, h->d_cref, h->d_k2p, ny, nc, nk);
-    CU(cudaGetLastError());
-    CU(cudaFreeAsync(dy, h->stream));
-    CU(cudaFreeAsync(dc, h->stream));
-    CU(cudaFreeAsync(dk, h->stream));
+    {
+        StagedF64 dy, dc, dk;
+        CU(dy.upload(y, ny, h->stream));
+        CU(dc.upload(tac_ref, nc, h->stream));
+        CU(dk.upload(k2p, nk, h->stream));
+        convert_data_kernel<<<(unsigned)((ny + 255) / 256), 256, 0, h->stream>>>(dy.p, dc.p, dk.p, h->d_y, h->d_cref, h->d_k2p, ny, nc, nk);
+        CU(cudaGetLastError());
+    }
     CU(cudaStreamSynchronize(h->stream));
     { int rc = check_data_range(h, n_tac); if (rc) { h->have_data = false; return rc; } }
     h->n_tac = n_tac;
@@ -466,14 +483,14 @@ extern "C" int petmh_set_data_f32(petmh_t* h, int n_tac, const float* y, const f
     }
     if (!h->have_noise) return fail(h, PETMH_EINVAL, "sigma_noise never set");
     const size_t ny = (size_t)n_tac * 48 * NT, nc = (size_t)n_tac * NT;
-    float* dc = nullptr;
-    CU(cudaMallocAsync(&dc, nc * sizeof(float), h->stream));
-    CU(cudaMemcpyAsync(h->d_y, y, ny * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(dc, tac_ref, nc * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->d_k2p, k2p, (size_t)n_tac * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    convert_data_f32_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, h->stream>>>(dc, h->d_cref, nc);
-    CU(cudaGetLastError());
-    CU(cudaFreeAsync(dc, h->stream));
+    {
+        Staged<float> dc;
+        CU(cudaMemcpyAsync(h->d_y, y, ny * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        CU(dc.upload(tac_ref, nc, h->stream));
+        CU(cudaMemcpyAsync(h->d_k2p, k2p, (size_t)n_tac * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        convert_data_f32_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, h->stream>>>(dc.p, h->d_cref, nc);
+        CU(cudaGetLastError());
+    }
     { int rc = check_data_range(h, n_tac); if (rc) { h->have_data = false; return rc; } }
     h->n_tac = n_tac;
     h->have_data = true;
@@ -630,6 +647,77 @@ extern "C" int petmh_philox_raw(petmh_t* h, uint64_t gid, uint32_t sweep, uint32
     philox_kernel<<<1, 64, 0, h->stream>>>(h->cfg.seed, gid, sweep, block, d);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, d, 48 * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return PETMH_OK;
+}
+
+// ---- the module-level helpers of kinetic_model.py on general grids (fp64; petmh_conv.cuh) ---------------------------
+namespace {
+int col_threads(int m) { return std::min(256, (m + 31) / 32 * 32); }
+}  // namespace
+
+extern "C" int petmh_interp1d_linear(petmh_t* h, int nx, const double* x, int np, const double* xp, const double* fp, int m,
+                                     double* out) {
+    if (!h || !x || !xp || !fp || !out) return fail(h, PETMH_EINVAL, "null argument");
+    if (nx < 1 || np < 2 || m < 1) return fail(h, PETMH_EINVAL, "need nx >= 1, np >= 2, m >= 1");
+    for (int i = 0; i < nx; i++)
+        if (!(x[i] <= xp[np - 1]))
+            return fail(h, PETMH_EINVAL, "x[%d] = %g lies beyond xp[-1] = %g (or is NaN): the reference indexes out of bounds there "
+                        "(IndexError, kinetic_model.py:46)", i, x[i], xp[np - 1]);
+    CU(cudaSetDevice(h->cfg.device));
+    StagedF64 dx, dxp, dfp, dout;
+    CU(dx.upload(x, nx, h->stream));
+    CU(dxp.upload(xp, np, h->stream));
+    CU(dfp.upload(fp, (size_t)np * m, h->stream));
+    CU(dout.alloc((size_t)nx * m, h->stream));
+    interp_rows_kernel<<<nx, col_threads(m), 0, h->stream>>>(dx.p, nx, dxp.p, np, dfp.p, m, dout.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, dout.p, (size_t)nx * m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return PETMH_OK;
+}
+
+extern "C" int petmh_continuous_convolution(petmh_t* h, int n, const double* x, const double* y0, const double* y1, int m,
+                                            int num_points, double* out) {
+    if (!h || !x || !y0 || !y1 || !out) return fail(h, PETMH_EINVAL, "null argument");
+    if (n < 2 || m < 1 || num_points < 0 || num_points == 1) return fail(h, PETMH_EINVAL, "need n >= 2, m >= 1, num_points 0 (= 2 n) or >= 2");
+    for (int i = 1; i < n; i++)
+        if (!(x[i] > x[i - 1])) return fail(h, PETMH_EINVAL, "x must be strictly increasing (x[%d] = %g, x[%d] = %g)", i - 1, x[i - 1], i, x[i]);
+    const int N = num_points ? num_points : 2 * n;                  // kinetic_model.py:13-16 (np.unique(x).size = n here)
+    CU(cudaSetDevice(h->cfg.device));
+    StagedF64 dx, dy0, dy1, dxrs, dy0rs, dy1rs, dconv, dout;
+    CU(dx.upload(x, n, h->stream));
+    CU(dy0.upload(y0, n, h->stream));
+    CU(dy1.upload(y1, (size_t)n * m, h->stream));
+    CU(dxrs.alloc(N, h->stream));
+    CU(dy0rs.alloc(N, h->stream));
+    CU(dy1rs.alloc((size_t)N * m, h->stream));
+    CU(dconv.alloc((size_t)N * m, h->stream));
+    CU(dout.alloc((size_t)n * m, h->stream));
+    const int T = col_threads(m);
+    conv_resample_kernel<<<N, T, 0, h->stream>>>(dx.p, n, dy0.p, dy1.p, m, N, dxrs.p, dy0rs.p, dy1rs.p);
+    CU(cudaGetLastError());
+    conv_discrete_kernel<<<N, T, 0, h->stream>>>(dxrs.p, dy0rs.p, dy1rs.p, m, N, dconv.p);
+    CU(cudaGetLastError());
+    conv_back_kernel<<<n, T, 0, h->stream>>>(dx.p, n, dxrs.p, N, dconv.p, m, dout.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, dout.p, (size_t)n * m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return PETMH_OK;
+}
+
+extern "C" int petmh_time_exponential(petmh_t* h, int np, const double* param, int nt, const double* t, double* out) {
+    if (!h || !param || !t || !out) return fail(h, PETMH_EINVAL, "null argument");
+    if (np < 1 || nt < 1) return fail(h, PETMH_EINVAL, "need np >= 1, nt >= 1");
+    CU(cudaSetDevice(h->cfg.device));
+    StagedF64 dp, dt, dout;
+    CU(dp.upload(param, np, h->stream));
+    CU(dt.upload(t, nt, h->stream));
+    const size_t n = (size_t)nt * np;
+    CU(dout.alloc(n, h->stream));
+    time_exponential_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(dp.p, np, dt.p, nt, dout.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, dout.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return PETMH_OK;
 }
@@ -1091,12 +1179,11 @@ extern "C" int petmh_get_ess_cross_chain(petmh_t* h, float* out) {
     if (h->cfg.max_draws <= 0 || n_stored < 2)
         return fail(h, PETMH_EINVAL, "cross-chain ESS needs stored draws (max_draws > 0, >= 2 draws stored; have %d)", n_stored);
     CU(cudaSetDevice(h->cfg.device));
-    float* d_out = nullptr;
-    CU(cudaMallocAsync(&d_out, (size_t)h->n_tac * 96 * sizeof(float), h->stream));
-    const int e = launch_tfp_ess(h->d_draws, h->n_tac, h->cfg.n_chains, h->cfg.max_draws, n_stored, d_out, h->stream);
-    if (e) { cudaFreeAsync(d_out, h->stream); return fail(h, PETMH_ECUDA, "tfp_ess: %s", cudaGetErrorString((cudaError_t)e)); }
-    CU(cudaMemcpyAsync(out, d_out, (size_t)h->n_tac * 96 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaFreeAsync(d_out, h->stream));
+    Staged<float> d_out;
+    CU(d_out.alloc((size_t)h->n_tac * 96, h->stream));
+    const int e = launch_tfp_ess(h->d_draws, h->n_tac, h->cfg.n_chains, h->cfg.max_draws, n_stored, d_out.p, h->stream);
+    if (e) return fail(h, PETMH_ECUDA, "tfp_ess: %s", cudaGetErrorString((cudaError_t)e));
+    CU(cudaMemcpyAsync(out, d_out.p, (size_t)h->n_tac * 96 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return PETMH_OK;
 }

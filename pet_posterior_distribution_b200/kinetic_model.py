@@ -1,12 +1,114 @@
-"""GPU-backed mirror of the part of the reference's kinetic_model.py that the MCMC path
-uses: class SRTM2 with the same constructor and ``create_activity_curve`` signature
-(kinetic_model.py:134-161).  The resample-convolve-interpolate "continuous convolution"
-(kinetic_model.py:12-32) runs on the B200 as the exact operator conv = M exp(-k2a t).
-No CPU fallback.
+"""GPU-backed mirror of the reference's kinetic_model.py: the classes SRTM2 and SRTM with the same constructors and
+``create_activity_curve`` / ``forward_model`` signatures (kinetic_model.py:62-84, 134-161) -- the resample-convolve-
+interpolate "continuous convolution" runs on the B200 as the exact operator conv = M exp(-k2a t) -- and the module-level
+helpers ``estimate_continuous_convolution`` (:12-32) and ``interp1d_linear_vec`` (:35-57) plus the classes' static
+``make_time_exponential`` / ``make_time_func`` / ``convolve`` (:89-128, :163-201) on general grids in fp64
+(csrc/petmh_conv.cuh).  No CPU fallback: every number comes from libpetmh.
 """
+import atexit
+import ctypes as C
+
 import numpy as np
 
+from . import _lib
 from .sampler import MHSampler
+
+_helpers = {}
+
+
+@atexit.register
+def _close_helpers():
+    while _helpers:
+        _helpers.popitem()[1].close()
+
+
+def _helper(device=0):
+    """One small handle per device for the stateless helper calls (they only need its device and stream)."""
+    if device not in _helpers:
+        _helpers[device] = MHSampler(n_chains=1, max_tacs=1, device=device)
+    return _helpers[device]
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def interp1d_linear_vec(x, xp, fp, dim=0, device=0):
+    """kinetic_model.interp1d_linear_vec (kinetic_model.py:35-57): linear interpolation of fp (given at xp, along axis
+    `dim`) at x, with the reference's weights (searchsorted node and its left neighbour; index -1 wraps for x <= xp[0]).
+    x beyond xp[-1] raises IndexError like the reference."""
+    x = np.ascontiguousarray(x, np.float64).reshape(-1)
+    xp = np.ascontiguousarray(xp, np.float64).reshape(-1)
+    fp = np.asarray(fp, np.float64)
+    f2 = fp.reshape(-1, 1) if fp.ndim == 1 else np.moveaxis(fp, dim, 0)
+    if f2.shape[0] != xp.size:
+        raise ValueError("fp has %d points along dim %d, xp has %d" % (f2.shape[0], dim, xp.size))
+    if x.size and not (x <= xp[-1]).all():
+        raise IndexError("index %d is out of bounds for axis 1 with size %d" % (xp.size, xp.size))
+    rest = f2.shape[1:]
+    f2 = np.ascontiguousarray(f2.reshape(xp.size, -1))
+    out = np.empty((x.size, f2.shape[1]), np.float64)
+    s = _helper(device)
+    s._ck(_lib.lib.petmh_interp1d_linear(s._h, x.size, _dp(x), xp.size, _dp(xp), _dp(f2), f2.shape[1], _dp(out)))
+    if fp.ndim == 1:
+        return out.reshape(x.size)
+    return np.moveaxis(out.reshape((x.size,) + rest), 0, dim)
+
+
+def estimate_continuous_convolution(x, y0, y1, num_points_resample=None, device=0):
+    """kinetic_model.estimate_continuous_convolution (kinetic_model.py:12-32): y0 (n,) convolved with every column of y1
+    ((n,) or (n, ...)) on the grid x: resampling onto num_points_resample (default 2 n) uniform points, truncated causal
+    discrete convolution times the spacing, interpolation back."""
+    x = np.ascontiguousarray(x, np.float64).reshape(-1)
+    y0 = np.ascontiguousarray(y0, np.float64).reshape(-1)
+    y1 = np.asarray(y1, np.float64)
+    if y0.size != x.size or y1.shape[0] != x.size:
+        raise ValueError("y0 and y1 must have len(x) points along axis 0")
+    N = 0 if num_points_resample is None else int(num_points_resample)
+    if y1.ndim > 1 and N % 2:       # scipy.ndimage.convolve1d (kinetic_model.py:28) has no origin -N//2 for an odd length
+        raise ValueError("Invalid origin; origin must satisfy -(len(weights) // 2) <= origin <= (len(weights)-1) // 2")
+    y2 = np.ascontiguousarray(y1.reshape(x.size, -1))
+    out = np.empty_like(y2)
+    s = _helper(device)
+    s._ck(_lib.lib.petmh_continuous_convolution(s._h, x.size, _dp(x), _dp(y0), _dp(y2), y2.shape[1], N, _dp(out)))
+    return out.reshape(y1.shape)
+
+
+def _make_time_func(param, time_vector, func, time_scale=None, space_scale=None):
+    """SRTM.make_time_func (kinetic_model.py:89-116): broadcast `func(param, t)` over a leading time axis and apply the
+    optional scales.  `func` is the caller's Python callable (host); the model classes use make_time_exponential."""
+    time_vector = np.asarray(time_vector, np.float64)
+    if np.isscalar(param):
+        output = func(param, time_vector)
+        if time_scale is not None:
+            output = output * time_scale
+        if space_scale is not None:
+            output = output * space_scale
+        return output
+    param = np.asarray(param, np.float64)
+    tshape = [-1] + [1] * param.ndim
+    output = func(param.reshape([1] + list(param.shape)), time_vector.reshape(tshape))
+    if time_scale is not None:
+        time_scale = np.asarray(time_scale)
+        output = output * (time_scale.reshape(tshape) if time_scale.ndim == 1 else time_scale)
+    if space_scale is not None:
+        space_scale = np.asarray(space_scale)
+        output = output * (space_scale if space_scale.ndim == output.ndim else space_scale[np.newaxis])
+    return output
+
+
+def _make_time_exponential(param, time_vector, time_scale=None, device=0, **kwargs):
+    """SRTM.make_time_exponential (kinetic_model.py:118-122): exp(param * t) with a leading time axis, on the GPU."""
+    t = np.ascontiguousarray(time_vector, np.float64).reshape(-1)
+    p = np.ascontiguousarray(np.atleast_1d(np.asarray(param, np.float64)))
+    flat = np.ascontiguousarray(p.reshape(-1))
+    out = np.empty((t.size, flat.size), np.float64)
+    s = _helper(device)
+    s._ck(_lib.lib.petmh_time_exponential(s._h, flat.size, _dp(flat), t.size, _dp(t), _dp(out)))
+    out = out[:, 0] if np.isscalar(param) else out.reshape((t.size,) + p.shape)
+    if time_scale is None and not kwargs:
+        return out
+    return _make_time_func(param, t, lambda *_: out, time_scale=time_scale, **kwargs)
 
 
 class SRTM2:
@@ -40,6 +142,9 @@ class SRTM2:
         return out[:, 0] if scalar else out
 
     __call__ = create_activity_curve
+    make_time_func = staticmethod(_make_time_func)                   # kinetic_model.py:163-196
+    make_time_exponential = staticmethod(_make_time_exponential)
+    convolve = staticmethod(lambda time_vector, c_0, c_1: estimate_continuous_convolution(time_vector, c_0, c_1))   # :198-201
 
 
 class SRTM:
@@ -66,3 +171,6 @@ class SRTM:
         return out[:, 0] if scalar else out
 
     __call__ = forward_model
+    make_time_func = staticmethod(_make_time_func)                   # kinetic_model.py:89-122
+    make_time_exponential = staticmethod(_make_time_exponential)
+    convolve = staticmethod(lambda time_vector, c_0, c_1: estimate_continuous_convolution(time_vector, c_0, c_1))   # :124-128

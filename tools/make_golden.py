@@ -9,7 +9,13 @@
   dataset_s0.1.npz        -- a 4-TAC test-style synthetic dataset from oracle/generator.py
                              (restated sample_sim_data.py), seed recorded.
 
-Run:  python tools/make_golden.py      (the GPU box never needs /root/reference)
+  kinetic_helpers_golden.npz -- inputs/outputs of the live reference's module-level helpers
+                             (estimate_continuous_convolution, interp1d_linear_vec,
+                             SRTM.make_time_exponential) on general grids: the pin for
+                             petmh_conv.cuh (CPU harness oracle/c/conv_check.cpp and the GPU path).
+
+Run:  python tools/make_golden.py            (everything; the GPU box never needs /root/reference)
+      python tools/make_golden.py helpers    (only kinetic_helpers_golden.npz)
 """
 import os
 import pickle
@@ -65,5 +71,50 @@ def main():
     print("wrote", os.listdir(OUT))
 
 
+def helpers():
+    import kinetic_model as km          # the live reference
+    from oracle import frames
+    t, _ = frames.frame_grid()
+    prior = pickle.load(open("/root/reference/prior_stats_nROI48.pik", "rb"))
+    rng = np.random.default_rng(20261019)
+    out = {}
+    # ---- estimate_continuous_convolution (kinetic_model.py:12-32): (x, y0, y1, num_points_resample or 0) ----
+    xg = np.sort(rng.uniform(0.0, 10.0, 17))
+    k2a = rng.uniform(0.004, 0.03, 48)
+    conv_cases = [
+        (t, np.abs(prior["mu_tac_ref"] * (1 + 0.1 * rng.standard_normal(54))), np.exp(-k2a[None, :] * t[:, None]), 0),
+        (xg, rng.standard_normal(17), rng.standard_normal((17, 3)), 0),
+        (xg, rng.standard_normal(17), rng.standard_normal((17, 5)), 64),
+        (xg, rng.standard_normal(17), rng.standard_normal(17), 51),          # 1-D y1: np.convolve path, odd length allowed
+        (t, np.abs(rng.standard_normal(54)), rng.standard_normal(54), 0),
+        (np.array([1.0, 2.5]), np.array([0.3, -1.0]), np.array([[2.0, 1.0], [0.5, -3.0]]), 0),   # the smallest grid
+    ]
+    for k, (x, y0, y1, N) in enumerate(conv_cases):
+        out["conv%d_x" % k], out["conv%d_y0" % k], out["conv%d_y1" % k], out["conv%d_N" % k] = x, y0, y1, N
+        out["conv%d_out" % k] = km.estimate_continuous_convolution(x, y0, y1, num_points_resample=N or None)
+    out["n_conv"] = len(conv_cases)
+    # ---- interp1d_linear_vec (kinetic_model.py:35-57), incl. x < xp[0] and x == xp[0] (index -1 wraps), nodes, x == xp[-1] ----
+    xp = np.sort(rng.uniform(-3.0, 7.0, 23))
+    interp_cases = [
+        (np.concatenate([[xp[0] - 2.0, xp[0] - 1e-9, xp[0], xp[4], xp[-1]], rng.uniform(xp[0], xp[-1], 40)]), xp, rng.standard_normal((23, 4))),
+        (rng.uniform(xp[0], xp[-1], 9), xp, rng.standard_normal(23)),
+        (np.linspace(t[0], t[-1], 108), t, rng.standard_normal((54, 48))),
+    ]
+    for k, (x, xp_, fp) in enumerate(interp_cases):
+        out["interp%d_x" % k], out["interp%d_xp" % k], out["interp%d_fp" % k] = x, xp_, fp
+        out["interp%d_out" % k] = km.interp1d_linear_vec(x, xp_, fp)
+    out["n_interp"] = len(interp_cases)
+    # ---- SRTM.make_time_exponential (kinetic_model.py:118-122) ----
+    out["texp_param"], out["texp_t"] = -k2a, t
+    out["texp_out"] = km.SRTM.make_time_exponential(-k2a, t)
+    out["texp_scalar_out"] = km.SRTM2.make_time_exponential(-0.0123, t)
+    np.savez_compressed(os.path.join(OUT, "kinetic_helpers_golden.npz"), **out)
+    print("wrote kinetic_helpers_golden.npz:", {k: np.shape(v) for k, v in out.items() if k.endswith("_out")})
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "helpers":
+        helpers()
+    else:
+        main()
+        helpers()
