@@ -17,10 +17,11 @@ from scipy import stats as spst
 from .frames import MK_HALF_T, frame_grid
 from .sampler import MHSampler
 
-# module-level configuration, same names as sample_sim_data.py:89-95
-n_samples = 100
+# module-level configuration, same names and defaults as sample_sim_data.py:88-95 (the shipped defaults write the
+# training set; mcmc.py reads a test set made with n_samples = 100, flag_testing_data = True)
+n_samples = 100000
 n_ROI = 48
-flag_testing_data = True
+flag_testing_data = False
 mean_sigma_noise_save = 1e-1
 alpha = 0.8
 
@@ -132,21 +133,26 @@ def load_prior(path=None):
     raise FileNotFoundError("prior_stats_nROI48 not found")
 
 
-def main():
-    """Write sim_data/nROI48/<ts>_{train,test}/data_*.pik + args_*.txt (sample_sim_data.py:218-240)."""
+def main(seed=None):
+    """Write sim_data/nROI48/<ts>_{train,test}/data_*.pik + args_*.txt (sample_sim_data.py:96-240): every step on the GPU
+    (K4), the test set with the Mahalanobis rule of :128-133.  seed: default the current time, like an unseeded run."""
     prior = load_prior()
-    sd = int(datetime.now().timestamp())
-    ds = generate(prior, n_samples, mean_sigma_noise_save, True, seed=sd, alpha_=alpha) if flag_testing_data else \
-        generate_gpu(prior, n_samples, mean_sigma_noise_save, seed=sd)
+    now = datetime.now()
+    sd = int(now.timestamp()) if seed is None else int(seed)
+    ds = generate_gpu(prior, n_samples, mean_sigma_noise_save, seed=sd, test_style=flag_testing_data, alpha_=alpha)
     str_test = "_test" if flag_testing_data else "_train"
     str_noise = "_s{:.1e}".format(mean_sigma_noise_save)
-    d = os.path.join("./sim_data", "nROI{}".format(n_ROI), datetime.now().strftime("%y-%m-%d_%H-%M-%S") + str_test)
+    save_samples_dir = os.path.join("./sim_data", "nROI{}".format(n_ROI))
+    d = os.path.join(save_samples_dir, now.strftime("%y-%m-%d_%H-%M-%S") + str_test)
     os.makedirs(d, exist_ok=True)
     pickle.dump(ds, open(os.path.join(d, "data_nROI{}_n{}{}.pik".format(n_ROI, n_samples, str_noise)), "wb"))
-    with open(os.path.join(d, "args_nROI{}_n{}{}.txt".format(n_ROI, n_samples, str_noise)), "wt") as f:
-        json.dump({"mean_sigma_noise": mean_sigma_noise_save, "MK_half_T": MK_HALF_T, "MK_lambda": np.log(2) / MK_HALF_T,
-                   "n_samples": n_samples, "n_ROI": n_ROI, "flag_mahalanobis": flag_testing_data}, f, indent=2, sort_keys=True)
+    names = ds["target_ROI_names"]
+    with open(os.path.join(d, "args_nROI{}_n{}{}.txt".format(n_ROI, n_samples, str_noise)), "wt") as f:   # :228-240
+        json.dump({"mean_sigma_noise": mean_sigma_noise_save, "target_ROI_names": None if names is None else [str(v) for v in names],
+                   "MK_half_T": MK_HALF_T, "MK_lambda": np.log(2) / MK_HALF_T, "n_samples": n_samples, "n_ROI": n_ROI,
+                   "save_samples_dir": save_samples_dir, "flag_mahalanobis": bool(flag_testing_data)}, f, indent=2, sort_keys=True)
     print("wrote", d)
+    return d
 
 
 if __name__ == "__main__":

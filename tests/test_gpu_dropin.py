@@ -80,6 +80,37 @@ def test_product_generator_schema(prior):
     assert np.abs(ds["tac_sampled"][2] / ds["dt"][None, :] / ref - 1).max() < 1e-5
 
 
+def test_generator_main_writes_reference_layout(tmp_path, monkeypatch, prior):
+    """sample_sim_data.py as a script (:96-240): sim_data/nROI48/<ts>_{train,test}/data_*.pik with the reference's schema
+    and args_*.txt, generated on the GPU; the test set obeys the Mahalanobis rule and feeds mcmc.find_test_file."""
+    import json
+    from scipy import stats
+    from pet_posterior_distribution_b200 import mcmc
+    from pet_posterior_distribution_b200 import sample_sim_data as gen
+    monkeypatch.chdir(tmp_path)
+    pickle.dump({k: prior[k] for k in prior}, open("prior_stats_nROI48.pik", "wb"))
+    keys = {"varDVR", "varR1", "vark2p", "vartacref", "tac_sampled", "tac_noisy_sampled", "mu_noise", "sigma_noise",
+            "mean_sigma_noise", "flag_mahalanobis", "target_ROI_names", "time_vector", "dt"}
+    for flag, n in ((False, 24), (True, 100)):
+        monkeypatch.setattr(gen, "n_samples", n)
+        monkeypatch.setattr(gen, "flag_testing_data", flag)
+        d = gen.main(seed=11)
+        assert os.path.basename(d).endswith("_test" if flag else "_train") and os.path.dirname(d).endswith(os.path.join("sim_data", "nROI48"))
+        ds = pickle.load(open(os.path.join(d, "data_nROI48_n%d_s1.0e-01.pik" % n), "rb"))
+        assert set(ds) == keys and len(ds["varDVR"]) == n and ds["flag_mahalanobis"] is flag
+        assert ds["tac_noisy_sampled"][0].shape == (48, 54) and ds["vartacref"][0].shape == (54,) and ds["sigma_noise"].shape == (48, 54)
+        assert all((np.asarray(ds[k]) >= 0).all() for k in ("varDVR", "varR1", "vartacref", "tac_sampled", "tac_noisy_sampled"))
+        a = json.load(open(os.path.join(d, "args_nROI48_n%d_s1.0e-01.txt" % n)))
+        assert set(a) == {"mean_sigma_noise", "target_ROI_names", "MK_half_T", "MK_lambda", "n_samples", "n_ROI", "save_samples_dir",
+                          "flag_mahalanobis"} and a["n_samples"] == n and a["flag_mahalanobis"] is flag
+        if flag:
+            dd = np.asarray(ds["varDVR"]) - prior["mu_DVR"]
+            d2 = np.einsum("ni,ij,nj->n", dd, np.linalg.inv(prior["Cov_DVR"]), dd)
+            assert (d2 < stats.chi2.ppf(0.8, 48) + 0.1).all()
+            found_dir, found_name = mcmc.find_test_file(os.path.join(str(tmp_path), "sim_data"))
+            assert os.path.samefile(found_dir, d) and found_name == "data_nROI48_n100_s1.0e-01.pik"
+
+
 def test_frame_grid_rejected_when_pattern_differs(prior):
     from pet_posterior_distribution_b200 import MHSampler, PetmhError
     s = MHSampler()

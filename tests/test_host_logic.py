@@ -19,6 +19,30 @@ def test_mcmc_module_keeps_reference_names():
     assert (mcmc.n_ROI_test, mcmc.n_samples_test, mcmc.iter_mcmc, mcmc.burn_mcmc, mcmc.chains) == (48, 100, 200, 400, 4)
 
 
+def test_generator_module_keeps_reference_names():
+    """sample_sim_data.py:88-95: same configuration names and shipped defaults (the training set)."""
+    from pet_posterior_distribution_b200 import sample_sim_data as gen
+    assert (gen.n_samples, gen.n_ROI, gen.flag_testing_data, gen.mean_sigma_noise_save, gen.alpha) == (100000, 48, False, 0.1, 0.8)
+    from pet_posterior_distribution_b200.frames import MK_HALF_T
+    assert MK_HALF_T == 109.8
+
+
+def test_kinetic_model_module_keeps_reference_names():
+    """kinetic_model.py's public surface: two module-level functions, SRTM and SRTM2 with their static helpers."""
+    from pet_posterior_distribution_b200 import kinetic_model as km
+    for name in ("estimate_continuous_convolution", "interp1d_linear_vec", "SRTM", "SRTM2"):
+        assert hasattr(km, name), name
+    for cls in (km.SRTM, km.SRTM2):
+        for name in ("make_time_func", "make_time_exponential", "convolve", "__call__"):
+            assert callable(getattr(cls, name)), (cls.__name__, name)
+    assert hasattr(km.SRTM, "forward_model") and hasattr(km.SRTM2, "create_activity_curve")
+    # make_time_func is host-side broadcasting around the caller's function (kinetic_model.py:89-116)
+    t, p = np.linspace(1, 5, 4), np.array([[0.1, 0.2], [0.3, 0.4]])
+    out = km.SRTM.make_time_func(p, t, lambda x, tt: x * tt, time_scale=np.arange(4.0) + 1, space_scale=np.full((2, 2), 2.0))
+    assert out.shape == (4, 2, 2) and np.allclose(out, p[None] * t[:, None, None] * (np.arange(4.0) + 1)[:, None, None] * 2.0)
+    assert np.allclose(km.SRTM2.make_time_func(0.5, t, lambda x, tt: x * tt, time_scale=3.0), 1.5 * t)
+
+
 def test_save_name_matches_reference_pattern():
     """mcmc.py:119-123 and the shipped file name MH_MCMC_nROI48_it2.0e+04_brn4.0e+04_km_obs-0.842-0.833-0.013.pik."""
     from pet_posterior_distribution_b200 import mcmc
