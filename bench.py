@@ -239,7 +239,9 @@ def run_b200(args):
     s = MHSampler(n_chains=C, max_tacs=S, max_draws=0, seed=2026, device=local, tac_gid0=rank * S)
     s.set_frames(t, dtv)
     s.set_prior(prior["mu_DVR"], prior["Cov_DVR"], prior["mu_R1"], prior["Cov_R1"])
+    t_syn = time.perf_counter()
     s.synth(S, 4321, prior["mu_tac_ref"], prior["Cov_tac_ref"], float(prior["mu_k2p"]), sig64)
+    t_syn = time.perf_counter() - t_syn                     # K4 (untimed set-up; reported in config.generator)
     g = s.synth_get(fields=("y", "tac_ref"))                # host copies (pinned) for the end-to-end leg
     y_pin = torch.empty((S, 48, 54), dtype=torch.float32, pin_memory=True)
     c_pin = torch.empty((S, 54), dtype=torch.float32, pin_memory=True)
@@ -420,7 +422,10 @@ def run_b200(args):
                        "tacs_per_gpu": S, "chains_per_tac": C, "sweeps_per_step": SW, "chain_steps_per_step": steps_per_step,
                        "l2_policy": "per-step working set (inputs+state %.1f GB) >> 126 MB L2" % ((S * 10588 + S * C * 3500) / 1e9),
                        "sec_per_48roi_posterior_60000_sweeps_amortised": 60000 * 96 * C / (value / world) ,
-                       "summary_finite": ok, "sec_per_48roi_posterior": cfg2, "chain_storage": store},
+                       "summary_finite": ok, "sec_per_48roi_posterior": cfg2, "chain_storage": store,
+                       "generator": {"what": "K4 petmh_synth: draws with positivity rejection, forward simulation, negative-TAC redraw, "
+                                             "truncated noise, all on the GPU (first call of the process: includes the module load)",
+                                     "tacs": S, "seconds": t_syn, "tacs_per_s": S / t_syn}},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "chain-steps/s", "h2d_bytes_per_step": int(S * (48 * 54 + 54 + 1) * 4) * world,
                     "d2h_bytes_per_step": int(S * 96 * 8 * 4) * world,
