@@ -268,7 +268,9 @@ def run_b200(args):
     stop, clk = threading.Event(), []
     th = threading.Thread(target=_clock_sampler, args=(stop, clk, local), daemon=True)
     th.start()
-    time.sleep(0.3)
+    t_w = time.perf_counter()                               # let nvidia-smi finish initialising (NVML enumerates every GPU of the
+    while not clk and time.perf_counter() - t_w < 5.0:     # box: up to a second on a fresh one) before the timed region starts --
+        time.sleep(0.05)                                    # its start-up, not its 200 ms polling, was seen to stall launches
     barrier()
     t0 = time.perf_counter()
     dev_ms, launches = 0.0, 0
