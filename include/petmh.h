@@ -225,6 +225,11 @@ int petmh_export_summary_inputs(petmh_t* h, void** d_draws, void** d_mom, void**
  * (main_script.py:807-810; TFP defaults: lags from the first negative autocorrelation on dropped).
  * Needs max_draws > 0 and >= 2 stored draws; one chain falls back to the single-chain formula. */
 int petmh_get_ess_cross_chain(petmh_t* h, float* out);
+/* cov[n_tac][2][48][48], corr[n_tac][2][48][48] f64 (either may be NULL; block 0 = DVR, 1 = R1): covariance (ddof = 1) and
+ * correlation across ROIs of the pooled stored draws, as the consumer forms them for its tables with
+ * np.cov(mcmc_res['DVR_mcmc'].reshape([-1, n_ROI]), rowvar=False) / np.corrcoef(...) (main_script.py:717-738).
+ * Needs max_draws > 0 and >= 2 pooled draws. */
+int petmh_get_posterior_cov(petmh_t* h, double* cov, double* corr);
 int petmh_get_state(petmh_t* h, float* q /*[n_tac][n_chains][96]*/, float* scale /*same*/);
 /* Warm start: overwrite every chain's position and scaling (either may be NULL), ZERO the tuning counters, the
  * accepted-move counters and the running moments, and set the sweep counter.  Not a resume -- see

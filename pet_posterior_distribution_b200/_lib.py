@@ -75,6 +75,7 @@ def _load():
         "petmh_export_summary_inputs": (C.c_int, [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                                   C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
         "petmh_get_ess_cross_chain": (C.c_int, [H, fp]),
+        "petmh_get_posterior_cov": (C.c_int, [H, dp, dp]),
         "petmh_get_state": (C.c_int, [H, fp, fp]),
         "petmh_set_state": (C.c_int, [H, fp, fp, C.c_int]),
         "petmh_checkpoint_bytes": (C.c_int64, [H]),

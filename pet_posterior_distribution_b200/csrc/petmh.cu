@@ -1188,6 +1188,26 @@ extern "C" int petmh_get_ess_cross_chain(petmh_t* h, float* out) {
     return PETMH_OK;
 }
 
+extern "C" int petmh_get_posterior_cov(petmh_t* h, double* cov, double* corr) {
+    if (!h || (!cov && !corr)) return fail(h, PETMH_EINVAL, "null argument");
+    int rc = check_ready(h);
+    if (rc) return rc;
+    const int ns = petmh_n_stored(h);
+    if (!h->d_draws || (size_t)h->cfg.n_chains * ns < 2)
+        return fail(h, PETMH_EINVAL, "the posterior covariance needs stored draws (max_draws > 0, >= 2 pooled draws; have %d per chain)", ns);
+    CU(cudaSetDevice(h->cfg.device));
+    const size_t n = (size_t)h->n_tac * 2 * 48 * 48;
+    StagedF64 dcov, dcorr;
+    CU(dcov.alloc(n, h->stream));
+    CU(dcorr.alloc(n, h->stream));
+    posterior_cov_kernel<<<(unsigned)h->n_tac * 2, 256, 0, h->stream>>>(h->d_draws, h->cfg.n_chains, h->cfg.max_draws, ns, dcov.p, dcorr.p);
+    CU(cudaGetLastError());
+    if (cov) CU(cudaMemcpyAsync(cov, dcov.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (corr) CU(cudaMemcpyAsync(corr, dcorr.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return PETMH_OK;
+}
+
 // ---- the k2-free SRTM as a sampled three-block model ------------------------------------------------
 extern "C" int petmh_srtm_sample(petmh_t* h, const double* mu_k2, const double* cov_k2, int draws, int tune, int thin,
                                  int n_tape_chains, int tape_tac, const float* tape_normals, const float* tape_logu,

@@ -431,6 +431,65 @@ done:
     return (int)e;
 }
 
+// ---- posterior covariance / correlation across ROIs (consumer side: main_script.py:717-738) ----------------------
+// np.cov(X, rowvar=False) (ddof = 1) and np.corrcoef(X, rowvar=False) of X = the pooled stored draws of one parameter block,
+// (chains * draws, 48): one CTA per (TAC, block).  Draws are centred on the fp64 column means, the products of a tile of
+// PC_TILE draws are summed with fp32 FMAs and the tiles in fp64 (as rd_ess does).
+constexpr int PC_TILE = 64;
+__global__ void __launch_bounds__(256) posterior_cov_kernel(const float* draws, int n_chains, int max_draws, int n_stored,
+                                                            double* cov /*[n_tac][2][48][48] or null*/, double* corr /*same*/) {
+    __shared__ double s_mean[48];
+    __shared__ double s_part[5][48];
+    __shared__ float s_x[PC_TILE][48];
+    __shared__ double s_cov[48 * 48];
+    const int tac = blockIdx.x >> 1, b = blockIdx.x & 1, tid = threadIdx.x;
+    const size_t n = (size_t)n_chains * n_stored;
+    auto row = [&](size_t k) {   // pooled draw k of this TAC: chain k / n_stored, stored slot k % n_stored
+        const size_t c = k / n_stored, d = k - c * n_stored;
+        return draws + (((size_t)tac * n_chains + c) * max_draws + d) * 96 + b * 48;
+    };
+    {   // column means: 5 groups of 48 threads stride over the draws
+        const int i = tid % 48, g = tid / 48;
+        if (g < 5) {
+            double s = 0.0;
+            for (size_t k = g; k < n; k += 5) s += (double)row(k)[i];
+            s_part[g][i] = s;
+        }
+        __syncthreads();
+        if (tid < 48) s_mean[tid] = ((s_part[0][tid] + s_part[1][tid]) + (s_part[2][tid] + s_part[3][tid]) + s_part[4][tid]) / (double)n;
+        __syncthreads();
+    }
+    double acc[9];               // 48 * 48 = 9 * 256 matrix entries: entry q = tid + 256 p
+#pragma unroll
+    for (int p = 0; p < 9; p++) acc[p] = 0.0;
+    for (size_t k0 = 0; k0 < n; k0 += PC_TILE) {
+        const int nt = (int)(n - k0 < (size_t)PC_TILE ? n - k0 : (size_t)PC_TILE);
+        for (int e = tid; e < nt * 48; e += 256) {
+            const int d = e / 48, i = e - d * 48;
+            s_x[d][i] = (float)((double)row(k0 + d)[i] - s_mean[i]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int p = 0; p < 9; p++) {
+            const int q = tid + 256 * p, i = q / 48, j = q - i * 48;
+            float a = 0.f;
+            for (int d = 0; d < nt; d++) a = fmaf(s_x[d][i], s_x[d][j], a);
+            acc[p] += (double)a;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int p = 0; p < 9; p++) s_cov[tid + 256 * p] = acc[p] / (double)(n - 1);
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < 9; p++) {
+        const int q = tid + 256 * p, i = q / 48, j = q - i * 48;
+        const size_t o = (size_t)blockIdx.x * (48 * 48) + q;
+        if (cov) cov[o] = s_cov[q];
+        if (corr) corr[o] = fmin(1.0, fmax(-1.0, s_cov[q] / sqrt(s_cov[i * 48 + i] * s_cov[j * 48 + j])));   // np.corrcoef clips too
+    }
+}
+
 // ---- TFP-style cross-chain ESS (consumer side: main_script.py:807-810) ----------------------
 // tfp.mcmc.effective_sample_size(x, cross_chain_dims) with its defaults, restated (PARITY UNPINNED:
 // tensorflow_probability is third-party and absent; checked against oracle/diagnostics.py

@@ -289,6 +289,14 @@ class MHSampler:
         self._ck(_lib.lib.petmh_get_ess_cross_chain(self._h, _f(out)))
         return out
 
+    def posterior_cov(self):
+        """(cov, corr), each (S, 2, 48, 48) float64 (block 0 = DVR, 1 = R1): np.cov / np.corrcoef of the pooled stored draws
+        across ROIs, the matrices main_script.py:717-738 builds from DVR_mcmc / R1_mcmc, on the GPU."""
+        cov = np.empty((self.n_tac, 2, N_ROI, N_ROI), np.float64)
+        corr = np.empty_like(cov)
+        self._ck(_lib.lib.petmh_get_posterior_cov(self._h, _d(cov), _d(corr)))
+        return cov, corr
+
     def summary_into(self, device_ptr, stream=None):
         """Write the (S,96,8) f32 summary to DEVICE memory (e.g. an all-gather slot)."""
         self._ck(_lib.lib.petmh_summary_device(self._h, C.c_void_p(int(device_ptr)),

@@ -103,3 +103,29 @@ def test_tfp_cross_chain_ess_matches_oracle(dataset, prior):
     s0.run(draws=50, tune=100)
     with pytest.raises(RuntimeError):
         s0.ess_cross_chain()
+
+
+def test_posterior_cov_matches_numpy(dataset, prior):
+    """petmh_get_posterior_cov == np.cov / np.corrcoef of the pooled stored draws (what main_script.py:717-738 computes from
+    DVR_mcmc / R1_mcmc), with unused draw slots (n_stored < max_draws) and a ragged last tile."""
+    from pet_posterior_distribution_b200 import PetmhError
+    s = make_sampler(dataset, prior, n_chains=3, max_draws=400, seed=9, tacs=[1, 3])
+    s.run(draws=331, tune=700)
+    dvr, r1 = s.chains()                              # (2, 3, 331, 48): 993 pooled draws = 15 tiles of 64 + 33
+    cov, corr = s.posterior_cov()
+    assert cov.shape == (2, 2, 48, 48) and corr.shape == cov.shape
+    for tac in range(2):
+        for b, arr in enumerate((dvr, r1)):
+            x = arr[tac].reshape(-1, 48).astype(np.float64)
+            ref, rc = np.cov(x, rowvar=False), np.corrcoef(x, rowvar=False)
+            sd = np.sqrt(np.diag(ref))
+            assert np.abs(cov[tac, b] - ref).max() <= 1e-5 * np.outer(sd, sd).max()
+            assert (np.abs(cov[tac, b] - ref) <= 1e-5 * np.outer(sd, sd) + 1e-300).all()
+            assert np.abs(corr[tac, b] - rc).max() < 1e-5 and np.abs(np.diag(corr[tac, b]) - 1).max() < 1e-6
+            assert np.array_equal(cov[tac, b], cov[tac, b].T)
+    s.close()
+    s0 = make_sampler(dataset, prior, n_chains=2, max_draws=0, tacs=[0])     # moments mode: no stored draws
+    s0.run(draws=10, tune=10)
+    with pytest.raises(PetmhError):
+        s0.posterior_cov()
+    s0.close()

@@ -28,7 +28,7 @@ n_sw = 6 if small else 24
 for wide, C, nt in (("0", 5, 2), ("1", 4, 1), ("2", 2, 1)):
     s = sampler(C, nt, 16, wide)
     s.run(draws=16, tune=n_sw)
-    s.chains(); s.summary(); s.summary_ext(); s.ess_cross_chain()
+    s.chains(); s.summary(); s.summary_ext(); s.ess_cross_chain(); s.posterior_cov()
     blob = s.checkpoint(); s.restore(blob); s.advance(0)
     s.close()
     print("sweep kernel wide", wide, "ok", flush=True)
