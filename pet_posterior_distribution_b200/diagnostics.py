@@ -31,13 +31,16 @@ def mcse_sd(x, ess_sd):
     return sd * fac
 
 
-def summary_csv(dvr, r1, k2p, gpu_summary, gpu_ext=None):
-    """CSV text with pm.summary's layout: rows var_DVR[i], var_R1[i], var_k2p; columns
-    mean, sd, hdi_3%, hdi_97%, mcse_mean, mcse_sd, ess_bulk, ess_tail, r_hat (default rounding:
-    3 decimals, ESS to 0 decimals, r_hat to 2).  dvr/r1: (chains, draws, 48); gpu_summary (96, 8) from
-    MHSampler.summary(), gpu_ext (96, 4) = hdi_3%, hdi_97%, mcse_sd, ess_sd from MHSampler.summary_ext()."""
-    out = io.StringIO()
-    out.write(",mean,sd,hdi_3%,hdi_97%,mcse_mean,mcse_sd,ess_bulk,ess_tail,r_hat\n")
+COLUMNS = ("mean", "sd", "hdi_3%", "hdi_97%", "mcse_mean", "mcse_sd", "ess_bulk", "ess_tail", "r_hat")
+_DECIMALS = {c: (0 if c.startswith("ess") else 2 if c == "r_hat" else 3) for c in COLUMNS}   # az.summary's default rounding
+
+
+def summary_table(dvr, r1, k2p, gpu_summary, gpu_ext=None):
+    """(row labels, (97, 9) float64 array) of pm.summary(idata): rows var_DVR[i], var_R1[i], var_k2p; columns COLUMNS,
+    unrounded.  dvr/r1: (chains, draws, 48); gpu_summary (96, 8) from MHSampler.summary(), gpu_ext (96, 4) = hdi_3%,
+    hdi_97%, mcse_sd, ess_sd from MHSampler.summary_ext().  The var_k2p row is what ArviZ reports for a constant
+    Deterministic (mcmc.py:150): sd and MCSE 0, ESS = chains * draws (a constant array's ESS is its size), r_hat NaN."""
+    labels, rows = [], []
     for b, (name, arr) in enumerate((("var_DVR", dvr), ("var_R1", r1))):
         for i in range(arr.shape[-1]):
             g = gpu_summary[b * 48 + i]
@@ -46,11 +49,29 @@ def summary_csv(dvr, r1, k2p, gpu_summary, gpu_ext=None):
             else:        # too few stored draws for the GPU path: numpy, with ess_sd ~ ess_bulk
                 lo, hi = hdi(arr[..., i])
                 msd = mcse_sd(arr[..., i], g[3])
-            out.write("%s[%d],%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.1f,%.1f,%.2f\n" %
-                      (name, i, g[0], g[1], lo, hi, g[2], msd, np.round(g[3]), np.round(g[4]), g[5]))
+            labels.append("%s[%d]" % (name, i))
+            rows.append([g[0], g[1], lo, hi, g[2], msd, g[3], g[4], g[5]])
     k = float(np.asarray(k2p).reshape(-1)[0])
-    out.write("var_k2p,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%s,%s,\n" % (k, 0.0, k, k, 0.0, 0.0, "", ""))
-    return out.getvalue()
+    n = float(np.prod(np.shape(dvr)[:2]))
+    labels.append("var_k2p")
+    rows.append([k, 0.0, k, k, 0.0, 0.0, n, n, np.nan])
+    return labels, np.asarray(rows, np.float64)
+
+
+def summary_csv(dvr, r1, k2p, gpu_summary, gpu_ext=None):
+    """The text of pm.summary(idata).to_csv() (mcmc.py:180-181): ArviZ's default rounding (3 decimals, ESS to 0, r_hat to
+    2) and pandas' own CSV formatting -- through pandas when it is importable, else the same shortest-repr floats."""
+    labels, tab = summary_table(dvr, r1, k2p, gpu_summary, gpu_ext)
+    try:
+        import pandas as pd
+        return pd.DataFrame(tab, index=labels, columns=list(COLUMNS)).round(_DECIMALS).to_csv()
+    except ImportError:
+        out = io.StringIO()
+        out.write("," + ",".join(COLUMNS) + "\n")
+        for lab, row in zip(labels, tab):
+            cells = ["" if np.isnan(v) else repr(round(float(v), _DECIMALS[c]) + 0.0) for c, v in zip(COLUMNS, row)]
+            out.write(lab + "," + ",".join(cells) + "\n")
+        return out.getvalue()
 
 
 def append_rhat_log(mcmc_dir, save_name, sample, gpu_summary, threshold=1.02):

@@ -79,9 +79,25 @@ def test_summary_csv_layout():
     lines = txt.strip().split("\n")
     assert lines[0] == ",mean,sd,hdi_3%,hdi_97%,mcse_mean,mcse_sd,ess_bulk,ess_tail,r_hat"
     assert len(lines) == 1 + 97 and lines[1].startswith("var_DVR[0],") and lines[49].startswith("var_R1[0],")
-    assert lines[97].startswith("var_k2p,0.013,")
+    assert lines[97] == "var_k2p,0.013,0.0,0.013,0.013,0.0,0.0,200.0,200.0,"      # a constant Deterministic in az.summary
     f = lines[1].split(",")
-    assert f[7] == "180.0" and f[8] == "151.0" and f[9] == "1.00"
+    assert f[2] == "0.01" and f[7] == "180.0" and f[8] == "151.0" and f[9] == "1.0"   # pandas' float formatting, ArviZ's rounding
+    import io
+    import pandas as pd
+    df = pd.read_csv(io.StringIO(txt), index_col=0)                               # what a consumer of _summary.csv does
+    assert list(df.columns) == list(diagnostics.COLUMNS) and df.shape == (97, 9) and df.loc["var_R1[3]", "r_hat"] == 1.0
+    # the pandas-free fallback writes the same text
+    import builtins, sys
+    real_import = builtins.__import__
+    def no_pandas(name, *a, **k):
+        if name == "pandas":
+            raise ImportError(name)
+        return real_import(name, *a, **k)
+    builtins.__import__ = no_pandas
+    try:
+        assert diagnostics.summary_csv(dvr, r1, [0.0126], g) == txt
+    finally:
+        builtins.__import__ = real_import
     lo, hi = diagnostics.hdi(rng.standard_normal(100000))
     assert abs(lo + 1.88) < 0.05 and abs(hi - 1.88) < 0.05
 
