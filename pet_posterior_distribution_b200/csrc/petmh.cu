@@ -77,6 +77,7 @@ struct petmh_handle {
     float last_ms = 0.f;
     int last_launches = 0;
     int launch_sweeps = 200;
+    bool launch_sweeps_env = false;   // PETMH_LAUNCH_SWEEPS given: no automatic choice
     int wide = -1;                // -1 auto, 0 never, 1 always three warps per chain pair, 2 always nine (PETMH_WIDE)
 };
 
@@ -269,7 +270,7 @@ extern "C" int petmh_create(const petmh_cfg* cfg, petmh_t** out) {
                     cfg->device);
     h = new petmh_handle();
     h->cfg = *cfg;
-    if (const char* e = getenv("PETMH_LAUNCH_SWEEPS")) h->launch_sweeps = std::max(1, atoi(e));
+    if (const char* e = getenv("PETMH_LAUNCH_SWEEPS")) { h->launch_sweeps = std::max(1, atoi(e)); h->launch_sweeps_env = true; }
     if (const char* e = getenv("PETMH_WIDE")) h->wide = std::max(0, std::min(2, atoi(e)));
     auto bail = [&](int code) { petmh_destroy(h); return code; };
 #define CUC(call)                                                                                     \
@@ -810,11 +811,19 @@ extern "C" int petmh_advance(petmh_t* h, int n_sweeps) {
     // of the moments mode; launches never straddle the tune / half / batch boundaries.
     const int n_half = h->plan_draws / 2, half1_at = h->plan_draws - n_half;
     const int blen = moments_batch_len(h->plan_draws);
+    // sweeps per launch: 200 keeps a launch of a full GPU near a second; a job of at most one wave that stores its draws runs
+    // 1000 (every launch rebuilds the per-TAC operators in its prologue: 1.7 % of a one-posterior job at 200 --
+    // profiles/r02_variant_probes.txt section 14).  Chains, states and stored-draw summaries do not depend on the chunking;
+    // the fp32 running moments do in their last bits (another merge order), so runs whose summary comes from the moments keep
+    // ONE chunking whatever their size: sharded and single-GPU results stay bit-identical there too.
+    const bool summary_from_draws =
+        h->cfg.max_draws > 0 && std::min(h->cfg.max_draws, (h->plan_draws + h->plan_thin - 1) / h->plan_thin) >= 8;
+    const int launch_sweeps = (h->launch_sweeps_env || grid > 2u * 148u || !summary_from_draws) ? h->launch_sweeps : 1000;
     int left = n_sweeps;
     h->last_launches = 0;
     CU(cudaEventRecord(h->ev0, h->stream));
     while (left > 0) {
-        int n = std::min(left, h->launch_sweeps);
+        int n = std::min(left, launch_sweeps);
         int half = -1, b_len = 0, b_idx = 0, b_end = 0;
         if (h->sweep < h->plan_tune) {
             n = std::min(n, h->plan_tune - h->sweep);
