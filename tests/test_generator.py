@@ -57,3 +57,23 @@ def test_mahalanobis_rule_matches_scipy(prior):
             assert neg.mean() > 0.3 and not mine[neg].any()          # negative forms are rejected, as in the reference
         else:
             assert (ref == mine).all() and 0.6 < mine.mean() < 0.95
+
+
+def test_product_host_draws_follow_the_test_set_rule(prior):
+    """sample_sim_data._mvn_positive (the product's host-side draws for generate(test_style=True)): every kept vector is
+    non-negative and passes the reference's rule, negative quadratic forms included (no GPU involved: pure numpy)."""
+    from scipy import stats
+    from pet_posterior_distribution_b200 import sample_sim_data as gen
+    rng = np.random.default_rng(4)
+    thr = stats.chi2.ppf(0.8, 48)
+    for k, n in (("DVR", 200), ("tac_ref", 60)):
+        mu, cov = prior["mu_" + k], prior["Cov_" + k]
+        inv = np.linalg.inv(cov)
+        x = gen._mvn_positive(rng, mu, cov, inv, n, True, 0.8, 48)
+        assert x.shape == (n, mu.size) and (x >= 0).all()
+        d2 = np.einsum("ij,jk,ik->i", x - mu, inv, x - mu)
+        assert (d2 >= 0).all() and (d2 < thr).all(), k
+        assert generator.mahalanobis_rule(x, mu, inv, 48, 0.8).mean() > 0.95      # (tac_ref: up to rounding of the ill-conditioned form)
+    free = gen._mvn_positive(rng, prior["mu_DVR"], prior["Cov_DVR"], np.linalg.inv(prior["Cov_DVR"]), 300, False, 0.8, 48)
+    d2 = np.einsum("ij,jk,ik->i", free - prior["mu_DVR"], np.linalg.inv(prior["Cov_DVR"]), free - prior["mu_DVR"])
+    assert 0.08 < (d2 >= thr).mean() < 0.35                                       # the training set keeps what the rule would drop
