@@ -87,8 +87,8 @@ def generate(prior, n_samples, mean_sigma_noise=0.1, test_style=False, seed=0, a
             "tac_sampled": tac_sampled, "tac_noisy_sampled": tac_noisy,
             "mu_noise": mu_noise, "sigma_noise": sigma_noise,
             "mean_sigma_noise": mean_sigma_noise, "flag_mahalanobis": test_style,
-            "target_ROI_names": prior["ROI_names"], "time_vector": t, "dt": dt,
-            "seed": seed}
+            "target_ROI_names": [str(v) for v in prior["ROI_names"]],      # a list of names in prior_stats_nROI48.pik
+            "time_vector": t, "dt": dt, "seed": seed}
 
 
 def model_from_dataset(ds, prior, sample):

@@ -45,6 +45,12 @@ def _mvn_positive(rng, mu, cov, cov_inv, n, test_style, alpha_, dof):
     return out[:n]
 
 
+def _roi_names(prior):
+    """target_ROI_names as the reference pickles it: the plain list of prior_stats_nROI48.pik (sample_sim_data.py:103,221)."""
+    names = prior.get("ROI_names")
+    return None if names is None else [str(v) for v in names]
+
+
 def _trunc_normal(rng, mean, std, low):
     a = (low - mean) / std
     return spst.truncnorm.rvs(a, np.inf, loc=mean, scale=std, random_state=rng)
@@ -84,7 +90,7 @@ def generate_gpu(prior, n, mean_sigma_noise=0.1, seed=0, device=0, sampler=None,
             "tac_sampled": list(g["tac_clean"].astype(np.float64) * dt[None, None, :]),
             "tac_noisy_sampled": list(g["y"].astype(np.float64) * dt[None, None, :]),
             "mu_noise": np.zeros_like(sigma_noise), "sigma_noise": sigma_noise, "mean_sigma_noise": mean_sigma_noise,
-            "flag_mahalanobis": bool(test_style), "target_ROI_names": prior.get("ROI_names"), "time_vector": t, "dt": dt}
+            "flag_mahalanobis": bool(test_style), "target_ROI_names": _roi_names(prior), "time_vector": t, "dt": dt}
 
 
 def generate(prior, n, mean_sigma_noise=0.1, test_style=False, seed=0, device=0, alpha_=0.8):
@@ -117,7 +123,7 @@ def generate(prior, n, mean_sigma_noise=0.1, test_style=False, seed=0, device=0,
             "vartacref": list(cref), "tac_sampled": list(tac * dt[None, None, :]),
             "tac_noisy_sampled": list(noisy * dt[None, None, :]), "mu_noise": np.zeros_like(sigma_noise),
             "sigma_noise": sigma_noise, "mean_sigma_noise": mean_sigma_noise, "flag_mahalanobis": test_style,
-            "target_ROI_names": prior.get("ROI_names"), "time_vector": t, "dt": dt}
+            "target_ROI_names": _roi_names(prior), "time_vector": t, "dt": dt}
 
 
 def load_prior(path=None):

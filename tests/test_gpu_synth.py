@@ -119,3 +119,31 @@ def test_test_style_mahalanobis_rule(prior, dataset):
     assert ds["flag_mahalanobis"] is True and len(ds["varDVR"]) == 8 and ds["tac_noisy_sampled"][0].shape == (48, 54)
     assert gen.generate_gpu(prior, 8, 0.1, seed=3)["flag_mahalanobis"] is False
     s.close()
+
+
+def test_distributions_match_the_live_reference(prior, dataset):
+    """K4 vs OUTPUTS OF THE REFERENCE ITSELF: tests/golden/reference_generated_stats.npz holds the per-coordinate mean / sd of the
+    DVR, R1 and reference-TAC draws that /root/reference/sample_sim_data.py kept in a 3000-sample training-style and a
+    1200-sample test-style run (tools/make_reference_generated.py), after its positivity, negative-TAC and Mahalanobis rules.
+    The GPU generator's kept draws have the same moments within Monte-Carlo error."""
+    import os
+    from pet_posterior_distribution_b200 import MHSampler
+    st = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_generated_stats.npz"))
+    n = 4096
+    s = MHSampler(n_chains=2, max_tacs=n, seed=1)
+    s.set_frames(dataset["time_vector"], dataset["dt"])
+    s.set_prior(prior["mu_DVR"], prior["Cov_DVR"], prior["mu_R1"], prior["Cov_R1"])
+    args = (prior["mu_tac_ref"], prior["Cov_tac_ref"], float(prior["mu_k2p"]), dataset["sigma_noise"])
+    for tag, alpha in (("train", None), ("test", 0.8)):
+        s.synth_test_rule(alpha, prior["Cov_DVR"], prior["Cov_R1"], prior["Cov_tac_ref"])
+        s.synth(n, 21, *args)
+        g = s.synth_get()
+        n_ref = int(st[tag + "_n"])
+        for key, okey in (("DVR", "varDVR"), ("R1", "varR1"), ("tac_ref", "vartacref")):
+            a = g[key].astype(np.float64)
+            mu, sd = st["%s_%s_mean" % (tag, okey)], st["%s_%s_sd" % (tag, okey)]
+            z = (a.mean(axis=0) - mu) / np.sqrt(sd ** 2 / n_ref + a.var(axis=0) / n)
+            assert np.abs(z).max() < 5.0 and np.sqrt((z ** 2).mean()) < 1.7, (tag, key, np.abs(z).max(), np.sqrt((z ** 2).mean()))
+            ratio = a.std(axis=0, ddof=1) / sd
+            assert np.abs(ratio - 1).max() < (0.1 if tag == "train" else 0.15), (tag, key, ratio.min(), ratio.max())
+    s.close()
