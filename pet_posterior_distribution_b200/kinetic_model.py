@@ -122,6 +122,15 @@ class SRTM2:
         ident = np.eye(48)
         self._s.set_prior(np.zeros(48), ident, np.zeros(48), ident)   # priors are not used by the forward model
 
+    # mcmc.py's Op holds its SRTM2 and is pickled to PyMC's worker processes (SURVEY.md 8 b): the object pickles as its
+    # three arrays and its device; the library handle is rebuilt on the other side.
+    def __getstate__(self):
+        return {"frame_time_list": self._frame_time_list, "frame_duration_list": self.frame_duration_list,
+                "tac_reference": self._tac_reference, "device": self._s.device}
+
+    def __setstate__(self, st):
+        self.__init__(st["frame_time_list"], st["frame_duration_list"], st["tac_reference"], device=st["device"])
+
     def _bind(self, k2p):
         if self._k2p != float(k2p):
             self._s.set_data(np.ones((1, 48, 54)), self._tac_reference[None], np.array([float(k2p)]), np.ones((48, 54)))
@@ -156,6 +165,12 @@ class SRTM:
         self._s = MHSampler(n_chains=1, max_tacs=1, device=device)
         self._s.set_frames(self._frame_time_list, self._frame_duration_list)
         self._s.set_prior(np.zeros(48), np.eye(48), np.zeros(48), np.eye(48))
+
+    def __getstate__(self):
+        return {"frame_time_list": self._frame_time_list, "frame_duration_list": self._frame_duration_list, "device": self._s.device}
+
+    def __setstate__(self, st):
+        self.__init__(st["frame_time_list"], st["frame_duration_list"], device=st["device"])
 
     def forward_model(self, DVR=None, k2=None, R1=None, tac_ref=None):
         scalar = np.isscalar(DVR)

@@ -34,6 +34,7 @@ class MHSampler:
         if rc:
             raise PetmhError(rc, (_lib.lib.petmh_last_error(None) or b"").decode())
         self.n_chains, self.max_tacs, self.max_draws = n_chains, max_tacs, max_draws
+        self.device = device
         self.n_tac = 0
 
     # -- plumbing -----------------------------------------------------------------------

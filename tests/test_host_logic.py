@@ -191,3 +191,34 @@ def test_two_rank_gloo_gather(tmp_path):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_model_objects_pickle_without_their_handle(monkeypatch):
+    """SURVEY.md 8 b: the reference's Op and its SRTM2 are pickled to PyMC's worker processes.  The mirrors pickle as their
+    arrays + device and rebuild the library handle on load (the handle itself, a ctypes pointer, cannot travel)."""
+    from pet_posterior_distribution_b200 import kinetic_model as km
+    from pet_posterior_distribution_b200 import mcmc
+    made = []
+
+    class FakeSampler:
+        def __init__(self, n_chains=4, max_tacs=1, max_draws=0, seed=0, device=0, tac_gid0=0):
+            self.device = device
+            made.append(self)
+
+        def set_frames(self, t, dt):
+            self.frames = (np.array(t), np.array(dt))
+
+        def set_prior(self, *a):
+            pass
+
+    monkeypatch.setattr(km, "MHSampler", FakeSampler)
+    t, dt, cr = np.linspace(1, 120, 54), np.full(54, 2.0), np.linspace(0.1, 5, 54)
+    m = km.SRTM2(frame_time_list=t, frame_duration_list=dt, tac_reference=cr, device=3)
+    op = mcmc.CreateTAC_SRTM2(m)
+    op2 = pickle.loads(pickle.dumps(op))
+    m2 = op2.k_srtm
+    assert isinstance(m2, km.SRTM2) and m2 is not m and len(made) == 2 and made[1].device == 3
+    assert np.array_equal(m2._tac_reference, cr) and np.array_equal(m2._frame_time_list, t) and m2._k2p is None
+    assert np.array_equal(made[1].frames[0], t) and np.array_equal(made[1].frames[1], dt)
+    s2 = pickle.loads(pickle.dumps(km.SRTM(frame_time_list=t, frame_duration_list=dt, device=1)))
+    assert isinstance(s2, km.SRTM) and made[-1].device == 1 and np.array_equal(s2._frame_duration_list, dt)
