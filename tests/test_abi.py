@@ -44,3 +44,30 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_null_handle_is_an_error_not_a_crash():
+    """Every entry point that takes a handle answers PETMH_EINVAL (or 0 for the two size queries) to a NULL handle -- an
+    error code, like the header promises, not a segmentation fault.  Run in a child process so that a regression fails
+    this test instead of killing the suite."""
+    import subprocess
+    import sys
+    code = r"""
+import ctypes as C, sys
+sys.path.insert(0, %r)
+from pet_posterior_distribution_b200 import _lib
+lib = C.CDLL(_lib.LIB_PATH)
+skip = ("petmh_create", "petmh_destroy", "petmh_version", "petmh_last_error")
+for n in _lib.EXPORTS:
+    if n in skip:
+        continue
+    f = getattr(lib, n); f.restype = C.c_int
+    rc = f(*([C.c_void_p(0)] * 11))
+    assert rc == (0 if n in ("petmh_n_stored", "petmh_checkpoint_bytes") else -1), (n, rc)
+lib.petmh_destroy(C.c_void_p(0))
+lib.petmh_last_error.restype = C.c_char_p
+lib.petmh_last_error(C.c_void_p(0))
+print("ok")
+""" % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), (r.returncode, r.stdout[-300:], r.stderr[-600:])
