@@ -71,3 +71,33 @@ print("ok")
 """ % ROOT
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), (r.returncode, r.stdout[-300:], r.stderr[-600:])
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/petmh.h is the boundary a C / cgo / cffi caller binds: it compiles as strict C99 (no C++, no torch types) and a
+    C program links against libpetmh.so and calls it (petmh_version; petmh_create fails with PETMH_ENODEVICE without a GPU)."""
+    import shutil
+    import subprocess
+    from pet_posterior_distribution_b200 import _lib
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    src = tmp_path / "t.c"
+    src.write_text('#include <stdio.h>\n#include "petmh.h"\n'
+                   'int main(void) {\n'
+                   '    petmh_cfg cfg = {0, 4, 1, 0, 0, 0};\n'
+                   '    petmh_t* h = NULL;\n'
+                   '    int rc = petmh_create(&cfg, &h);\n'
+                   '    printf("%d %d %s\\n", petmh_version(), rc, rc ? petmh_last_error(NULL) : "created");\n'
+                   '    if (!rc) petmh_destroy(h);\n'
+                   '    return 0;\n}\n')
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = tmp_path / "t"
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-l:" + os.path.basename(_lib.LIB_PATH), "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120, check=True).stdout.split(None, 2)
+    assert int(out[0]) >= 100
+    import torch
+    if not torch.cuda.is_available():
+        assert int(out[1]) == -2 and "no CPU fallback" in out[2]
+    else:
+        assert int(out[1]) == 0
