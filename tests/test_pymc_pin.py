@@ -11,8 +11,9 @@ def _reference_model(pm, pt, m):
     """The model block of mcmc.py:147-155 for one golden TAC, with the forward model as a pytensor Op that calls the
     pinned numpy restatement of kinetic_model.SRTM2.create_activity_curve (mcmc.py:27-39)."""
     from oracle import forward
+    from pytensor.graph.op import Op                       # mcmc.py:12
 
-    class CreateTAC(pt.Op):
+    class CreateTAC(Op):
         itypes = [pt.dvector, pt.dvector, pt.dscalar]
         otypes = [pt.dmatrix]
 
