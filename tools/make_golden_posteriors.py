@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 G = os.path.join(ROOT, "tests", "golden")
 TUNE, DRAWS, CHAINS = 5000, 30000, 16
-CASES = (("0.05", 0), ("0.1", 2), ("0.2", 0), ("0.2", 1))
+CASES = (("0.05", 0), ("0.1", 2), ("0.2", 0), ("0.2", 1), ("0.1", 0))   # (the last one for tests/test_independent_posterior.py)
 
 
 def dataset(sig):
@@ -41,7 +41,10 @@ def main():
     from oracle import cmh, diagnostics as dg
     from oracle.logp import Model
     pr = np.load(os.path.join(G, "prior_stats_nROI48.npz"))
+    only = sys.argv[1:]                                   # e.g. "0.1:0" to (re)make one case
     for sig, tac in CASES:
+        if only and "%s:%d" % (sig, tac) not in only:
+            continue
         ds = dataset(sig)
         y = ds["tac_noisy_sampled"][tac] / ds["dt"][None, :]
         m = Model(ds["time_vector"], ds["vartacref"][tac], ds["vark2p"][tac], y, ds["sigma_noise"],
