@@ -169,7 +169,7 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------
 def _ncu_dram_traffic(S, SW, launch_ms):
     """roofline.traffic = dram__bytes_read.sum + dram__bytes_write.sum of ONE mh_sweep_kernel launch of the default
-    workload, from the ncu capture of this round's kernel committed under profiles/ (tools/capture_bench_dram.sh).  Used
+    workload, from the ncu capture of this round's kernel committed under profiles/ (tools/capture_bench_profiles.sh).  Used
     only if the capture is of the same kernel, the same workload and a launch time within 25 % of the one measured now
     (ncu serialises and runs cold, so the times do not agree exactly); else None."""
     import csv
