@@ -18,22 +18,25 @@ CASES = [("0.1", 0, "oracle_posterior_s0.1_tac0.npz"), ("0.2", 0, "oracle_poster
 
 @pytest.mark.parametrize("sigma,tac,oracle_file", CASES)
 def test_oracle_posterior_matches_independent_sampler(sigma, tac, oracle_file):
+    """Two oracle runs per case against the independent sampler (8 chains x 1 M steps): the 16 x 30 000-draw golden the GPU
+    sampler is compared with, and a 64 x 30 000-draw run (oracle_posterior_long_*) that resolves 1-2 % of a posterior SD."""
     ind = np.load(os.path.join(GOLDEN, "independent_posterior_s%s_tac%d.npz" % (sigma, tac)))
-    ref = np.load(os.path.join(GOLDEN, oracle_file))
-    assert int(ref["tac"]) == tac == int(ind["tac"])
     # the independent run itself has converged and is long enough to resolve a shift of a fraction of a posterior SD
-    assert ind["rhat"].max() < 1.01 and ind["ess_bulk"].min() > 3000
+    assert ind["rhat"].max() < 1.01 and ind["ess_bulk"].min() > 20000
     assert 0.15 < ind["accept_rate"].mean() < 0.35                      # random-walk Metropolis near its optimum
-    res = np.sqrt(ind["mcse_mean"] ** 2 + ref["mcse_mean"] ** 2) / ref["sd"]
-    assert res.max() < 0.04                                             # combined MCSE <= 4 % of the posterior SD
     rms = lambda z: float(np.sqrt((z ** 2).mean()))
-    z_mean = (ind["mean"] - ref["mean"]) / np.sqrt(ind["mcse_mean"] ** 2 + ref["mcse_mean"] ** 2)
-    z_sd = (ind["sd"] - ref["sd"]) / np.sqrt(ind["mcse_sd"] ** 2 + ref["mcse_sd"] ** 2)
-    assert np.abs(z_mean).max() < 4.0 and rms(z_mean) < 1.4, (np.abs(z_mean).max(), rms(z_mean))
-    assert np.abs(z_sd).max() < 4.0 and rms(z_sd) < 1.4, (np.abs(z_sd).max(), rms(z_sd))
-    # in absolute terms: every posterior mean within 0.1 posterior SD, every SD within 5 %
-    assert (np.abs(ind["mean"] - ref["mean"]) / ref["sd"]).max() < 0.1
-    assert np.abs(ind["sd"] / ref["sd"] - 1).max() < 0.05
+    for fname, res_max, mean_tol, sd_tol in ((oracle_file, 0.035, 0.08, 0.04), ("oracle_posterior_long_s%s_tac%d.npz" % (sigma, tac), 0.02, 0.05, 0.02)):
+        ref = np.load(os.path.join(GOLDEN, fname))
+        assert int(ref["tac"]) == tac == int(ind["tac"])
+        res = np.sqrt(ind["mcse_mean"] ** 2 + ref["mcse_mean"] ** 2) / ref["sd"]
+        assert res.max() < res_max, (fname, res.max())                 # combined MCSE as a fraction of the posterior SD
+        z_mean = (ind["mean"] - ref["mean"]) / np.sqrt(ind["mcse_mean"] ** 2 + ref["mcse_mean"] ** 2)
+        z_sd = (ind["sd"] - ref["sd"]) / np.sqrt(ind["mcse_sd"] ** 2 + ref["mcse_sd"] ** 2)
+        assert np.abs(z_mean).max() < 4.0 and rms(z_mean) < 1.4, (fname, np.abs(z_mean).max(), rms(z_mean))
+        assert np.abs(z_sd).max() < 4.0 and rms(z_sd) < 1.4, (fname, np.abs(z_sd).max(), rms(z_sd))
+        # in absolute terms: every posterior mean within mean_tol posterior SDs, every SD within sd_tol
+        assert (np.abs(ind["mean"] - ref["mean"]) / ref["sd"]).max() < mean_tol, fname
+        assert np.abs(ind["sd"] / ref["sd"] - 1).max() < sd_tol, fname
 
 
 def test_independent_target_equals_oracle_logp(models, dataset, prior):

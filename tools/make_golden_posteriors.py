@@ -41,7 +41,9 @@ def main():
     from oracle import cmh, diagnostics as dg
     from oracle.logp import Model
     pr = np.load(os.path.join(G, "prior_stats_nROI48.npz"))
-    only = sys.argv[1:]                                   # e.g. "0.1:0" to (re)make one case
+    only = [a for a in sys.argv[1:] if a != "--long"]     # e.g. "0.1:0" to (re)make one case
+    long_run = "--long" in sys.argv[1:]                   # 64 chains instead of 16 -> oracle_posterior_long_*.npz (CPU-side checks only)
+    chains = 64 if long_run else CHAINS
     for sig, tac in CASES:
         if only and "%s:%d" % (sig, tac) not in only:
             continue
@@ -49,15 +51,15 @@ def main():
         y = ds["tac_noisy_sampled"][tac] / ds["dt"][None, :]
         m = Model(ds["time_vector"], ds["vartacref"][tac], ds["vark2p"][tac], y, ds["sigma_noise"],
                   pr["mu_DVR"], pr["Cov_DVR"], pr["mu_R1"], pr["Cov_R1"])
-        draws, _ = cmh.CModel(m).run_free(CHAINS, TUNE, DRAWS, seed=4242 + tac, keep=True)
-        x = draws[:, TUNE:].reshape(CHAINS, DRAWS, 96).astype(np.float64)
+        draws, _ = cmh.CModel(m).run_free(chains, TUNE, DRAWS, seed=4242 + tac + (77 if long_run else 0), keep=True)
+        x = draws[:, TUNE:].reshape(chains, DRAWS, 96).astype(np.float64)
         out = dict(mean=x.mean(axis=(0, 1)), sd=x.std(axis=(0, 1), ddof=1),
                    mcse_mean=np.array([dg.mcse_mean(x[:, :, k]) for k in range(96)]),
                    mcse_sd=np.array([dg.mcse_sd(x[:, :, k]) for k in range(96)]),
                    rhat=np.array([dg.rhat_rank(x[:, :, k]) for k in range(96)]),
                    ess_bulk=np.array([dg.ess_bulk(x[:, :, k]) for k in range(96)]),
-                   tune=TUNE, draws=DRAWS, chains=CHAINS, tac=tac, sigma=float(sig))
-        path = os.path.join(G, "oracle_posterior_s%s_tac%d.npz" % (sig, tac))
+                   tune=TUNE, draws=DRAWS, chains=chains, tac=tac, sigma=float(sig))
+        path = os.path.join(G, "oracle_posterior_%ss%s_tac%d.npz" % ("long_" if long_run else "", sig, tac))
         np.savez_compressed(path, **out)
         print("%s: rhat max %.3f  ess_bulk min %.0f  sd median %.4f" % (os.path.basename(path), out["rhat"].max(), out["ess_bulk"].min(),
                                                                          np.median(out["sd"])))

@@ -16,7 +16,7 @@ Metropolis kernel with frozen scaling has the model's posterior as its stationar
 
 Writes tests/golden/independent_posterior_s{sigma}_tac{k}.npz (mean, sd, their MCSEs, r_hat, ESS, acceptance rate).
 tests/test_independent_posterior.py compares the oracle's golden posteriors with them; the GPU sampler is compared with the
-oracle's in tests/test_gpu_posterior.py.  Needs /root/reference (build container only); ~4 min per case on 8 cores.
+oracle's in tests/test_gpu_posterior.py.  Needs /root/reference (build container only); ~25 min per case on 8 cores.
 """
 import multiprocessing as mp
 import os
@@ -29,8 +29,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, "/root/reference")
 G = os.path.join(ROOT, "tests", "golden")
-CASES = (("0.1", 0, "oracle_posterior_tac0.npz"), ("0.2", 0, "oracle_posterior_s0.2_tac0.npz"))
-STEPS, BURN, THIN = 280000, 30000, 50
+CASES = (("0.1", 0, "oracle_posterior_s0.1_tac0.npz"), ("0.2", 0, "oracle_posterior_s0.2_tac0.npz"))
+STEPS, BURN, THIN = 1030000, 30000, 50
 
 
 def load_case(sig, tac):
