@@ -73,3 +73,33 @@ def test_compiled_schedule_matches_oracle_pattern():
     assert used.size == 1122 and np.unique(used).size == 1122
     rows, cols = used >> 6, used & 63
     assert all(cols[i] < nrow[rows[i]] for i in range(used.size))
+
+
+import os as _os
+import pytest as _pytest
+
+
+@_pytest.mark.skipif(not _os.path.isfile("/root/reference/kinetic_model.py"), reason="the live reference exists in the build container only")
+def test_golden_regenerates_from_the_live_reference(forward_golden):
+    """Provenance: the LIVE /root/reference kinetic_model.py, called on the fixture's inputs, returns the fixture's outputs bit
+    for bit (SRTM2.create_activity_curve, estimate_continuous_convolution, SRTM.forward_model).  Child process: keeps the
+    reference's module names out of this one."""
+    import subprocess
+    import sys
+    path = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden", "forward_golden.npz")
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, "/root/reference")
+import kinetic_model as km
+g = np.load(%r)
+t, dt = g["t"], g["dt"]
+for c in range(g["c_r"].shape[0]):
+    m = km.SRTM2(frame_time_list=t, frame_duration_list=dt, tac_reference=g["c_r"][c])
+    assert np.array_equal(m.create_activity_curve(DVR=g["DVR"][c], R1=g["R1"][c], k2p=g["k2p"][c]), g["tac"][c]), c
+    assert np.array_equal(km.estimate_continuous_convolution(t, g["c_r"][c], np.eye(54)), g["M"][c]), c
+    s = km.SRTM(frame_time_list=t, frame_duration_list=dt)
+    assert np.array_equal(s.forward_model(DVR=g["DVR"][c], k2=g["k2"][c], R1=g["R1"][c], tac_ref=g["c_r"][c]), g["tac_srtm"][c]), c
+print("ok")
+""" % path
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), (r.stdout[-300:], r.stderr[-800:])

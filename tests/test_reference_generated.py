@@ -156,3 +156,28 @@ def test_noise_level_per_roi(ref_stats):
     assert sp.ks_2samp(mine, sr).pvalue > 1e-3
     orc = generator.trunc_normal(np.random.default_rng(3), 0.1, 0.03, low=0, size=1920)
     assert sp.ks_2samp(orc, sr).pvalue > 1e-3
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/sample_sim_data.py"), reason="the live reference exists in the build container only")
+def test_fixture_regenerates_from_the_live_reference():
+    """Provenance: exec'ing /root/reference/sample_sim_data.py again (same numpy global seed) reproduces the committed
+    test-style fixture bit for bit.  Child process: the runner installs stub modules for matplotlib / diffusion_model."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import sys, io, contextlib, numpy as np
+sys.path.insert(0, %r)
+sys.path.insert(0, %r + "/tools")
+import make_reference_generated as mk
+ref = np.load(%r)
+seed = int(ref["numpy_global_seed"])
+with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+    d = mk.run_reference_script(6, True, 0.1, seed)
+a = mk.as_arrays(d, seed)
+for k in ("varDVR", "varR1", "vartacref", "tac_sampled", "tac_noisy_sampled", "sigma_noise"):
+    assert np.array_equal(a[k], ref[k]), k
+print("ok")
+""" % (root, root, os.path.join(GOLDEN, "reference_generated_test_s0.1.npz"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), (r.stdout[-300:], r.stderr[-800:])
