@@ -50,3 +50,27 @@ def test_convolution_elements_match_reference(chk, gold):
         out = np.empty_like(y2)
         chk.conv_check_convolution(x.size, _d(x), _d(y0), _d(y2), y2.shape[1], N, _d(out))
         assert np.abs(out.reshape(ref.shape) - ref).max() <= 1e-12 * np.abs(ref).max(), k
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/kinetic_model.py"), reason="the live reference exists in the build container only")
+def test_helper_golden_regenerates_from_the_live_reference():
+    """Provenance: the LIVE /root/reference kinetic_model.py helpers, called on the fixture's inputs, return the fixture's
+    outputs bit for bit (estimate_continuous_convolution, interp1d_linear_vec, make_time_exponential)."""
+    import sys
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, "/root/reference")
+import kinetic_model as km
+g = np.load(%r)
+for k in range(int(g["n_conv"])):
+    N = int(g["conv%%d_N" %% k])
+    out = km.estimate_continuous_convolution(g["conv%%d_x" %% k], g["conv%%d_y0" %% k], g["conv%%d_y1" %% k], num_points_resample=N or None)
+    assert np.array_equal(out, g["conv%%d_out" %% k]), ("conv", k)
+for k in range(int(g["n_interp"])):
+    out = km.interp1d_linear_vec(g["interp%%d_x" %% k], g["interp%%d_xp" %% k], g["interp%%d_fp" %% k])
+    assert np.array_equal(out, g["interp%%d_out" %% k]), ("interp", k)
+assert np.array_equal(km.SRTM.make_time_exponential(g["texp_param"], g["texp_t"]), g["texp_out"])
+print("ok")
+""" % os.path.join(ROOT, "tests", "golden", "kinetic_helpers_golden.npz")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), (r.stdout[-300:], r.stderr[-800:])
